@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the DDNeRF / mip-NeRF per-ray hot path (BASELINE.json metric: train rays/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--workload cfg2|cfg1|cfg4] [--mlp-mode bf16|fp32]
+
+One "step" = one training iteration of train_model.py:135-177 (run_iter on a ray batch, loss,
+backward, Adam) on synthetic dataset-shaped rays and seeded random-init weights.  N=1 runs the
+configuration BASELINE.json quotes for one B200: config_blender_mipnerf.yml, 4096 rays,
+128+128 samples (cfg2).  N>1 (torchrun, one rank per GPU): same per-GPU batch, rays sharded by
+rank, one NCCL all-reduce of the flat gradient bucket per step (weak scaling).
+
+`--impl reference` times the CPU restatement of the reference (oracle/ddnerf_oracle.py, pinned to
+the reference by tests/test_oracle_golden.py) on the host cores, on a bounded sample of the same
+workload; the reference itself is pure PyTorch and cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (preset, overrides, rays per GPU, description)
+    "cfg2": ("config_blender_mipnerf", dict(num_coarse=128, num_fine=128), 4096,
+             "config_blender_mipnerf.yml mip-NeRF IPE coarse/fine 128+128 samples, 4096-ray batch train step"),
+    "cfg1": ("config_blender", dict(), 1024, "config_blender.yml DDNeRF 32+32 samples, 1024-ray batch train step"),
+    "cfg4": ("config_360", dict(), 16384, "config_360.yml DDNeRF 32+32 samples, 16384 rays/GPU train step"),
+}
+MACS_TRAIN = {4: 610304 * 2 + 557696, 6: 610560 * 2 + 557696 + 2 * 128}   # fwd + dW + dX MACs per sample row
+
+
+def mlp_flops_per_step(cfg, n_rays):
+    """Algorithmic MLP FLOPs of one train step (3.557 MFLOP/sample, both passes)."""
+    s0, s1 = cfg.nerf.train.num_coarse, cfg.nerf.train.num_fine
+    is_dd = cfg.nerf.type == "DDNerfModel"
+    return 2.0 * n_rays * (s0 * MACS_TRAIN[6 if is_dd else 4] + s1 * MACS_TRAIN[4])
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batches(kind, n_rays, count, rank, near, far):
+    """`count` host batches (pinned) of dataset-shaped rays + random targets."""
+    from ddnerf_b200.rays import synth_rays
+    batches = []
+    for b in range(count):
+        ro, rd, rad, _, _ = synth_rays(kind, n_rays, seed=97 * rank + b)
+        tgt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(5000 + 97 * rank + b))
+        batches.append(tuple(t.pin_memory() if torch.cuda.is_available() else t for t in (ro, rd, rad, tgt)))
+    return batches
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_baseline(cfg, kind, n_rays, steps, warmup):
+    """The oracle's train step (fwd + bwd) on host cores; rays/s."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.rays import synth_rays
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    is_dd = cfg.nerf.type == "DDNerfModel"
+    tp = cfg.train_params
+    ocfg = orc.PathConfig(model=cfg.nerf.type, near=cfg.dataset.near, far=cfg.dataset.far,
+                          num_coarse=cfg.nerf.train.num_coarse, num_fine=cfg.nerf.train.num_fine, perturb=True,
+                          noise_std=cfg.nerf.train.radiance_field_noise_std, blender=cfg.dataset.type.lower() == "blender",
+                          pdf_padding=tp.pdf_padding, gaussian_smooth_factor=tp.gaussian_smooth_factor,
+                          dist_reg_coeficient=tp.dist_reg_coeficient, loss_coeficients=tp.loss_coeficients,
+                          dp_coeficient=tp.dp_coeficient)
+    pc = orc.init_mlp_params(is_dd, seed=42)
+    pf = orc.init_mlp_params(False, seed=43) if is_dd else None
+    ro, rd, rad, _, _ = synth_rays(kind, n_rays, seed=1)
+    rays = orc.pack_rays(ro, rd, rad, ocfg.near, ocfg.far)
+    g = torch.Generator().manual_seed(0)
+    tgt = torch.rand(n_rays, 3, generator=g)
+    s0, s1 = ocfg.num_coarse, ocfg.num_fine
+    times = []
+    for it in range(warmup + steps):
+        rnd = dict(t_rand=torch.rand(n_rays, s0 + 1, generator=g), noise0=torch.randn(n_rays, s0, generator=g),
+                   u_rand=torch.rand(n_rays, s1 + 1, generator=g), noise1=torch.randn(n_rays, s1, generator=g))
+        t0 = time.perf_counter()
+        orc.train_step(ocfg, pc, pf, rays, tgt, rnd)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_rays / sec, sec, threads
+
+
+def run_reference(args, cfg, kind, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(args.cpu_rays, WORKLOADS[args.workload][2])
+    rps, sec, threads = cpu_baseline(cfg, kind, n, args.steps, max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": "train_rays_per_sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc},
+            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{n}-ray batch of the workload per step, fwd+bwd, torch CPU fp32 oracle"},
+            "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mlp-mode", default=os.environ.get("DDNERF_MLP_MODE", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from ddnerf_b200.config import preset
+    pname, over, n_rays, desc = WORKLOADS[args.workload]
+    cfg, kind = preset(pname, **over)
+
+    if args.impl == "reference":
+        run_reference(args, cfg, kind, desc)
+        return
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    os.environ["DDNERF_MLP_MODE"] = args.mlp_mode
+    from ddnerf_b200 import _lib, ops
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.trainer import Trainer
+    lib = _lib.load()
+
+    torch.manual_seed(cfg.experiment.randomseed)                       # identical weights on every rank
+    model = getattr(M, cfg.nerf.type)(cfg)
+    model.to(dev)
+    for net in {id(model.coarse): model.coarse, id(model.fine): model.fine}.values():
+        net.mlp_mode = args.mlp_mode
+    trainer = Trainer(model, distributed=world > 1)
+    torch.manual_seed(1234 + rank)                                     # per-rank draws inside the path
+
+    K, W = args.steps, max(args.warmup, 3)
+    host = make_batches(kind, n_rays, min(K, 8), rank, cfg.dataset.near, cfg.dataset.far)
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, count):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(count):
+            run_step(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- kernel-resident arm: inputs already in HBM ------------------------------------------
+    def step_resident(s):
+        trainer.step(*resident[s % len(resident)])
+
+    for s in range(W):
+        step_resident(s)
+    ops.MLP_TIMING = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.ddnerf_launch_count()
+    ms_total = timed(step_resident, K)
+    launches = lib.ddnerf_launch_count() - l0
+    clocks = sampler.stop()
+    mlp_events, ops.MLP_TIMING = ops.MLP_TIMING, None
+    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events)
+    mlp_calls = len(mlp_events)
+
+    # ---- end-to-end arm: pinned host rays -> device every step, loss read back every step ----
+    stage = [torch.empty_like(t, device=dev) for t in host[0]]
+    loss_host = torch.empty(3, pin_memory=True)
+
+    def step_e2e(s):
+        for dst, src in zip(stage, host[s % len(host)]):
+            dst.copy_(src, non_blocking=True)
+        loss, mse = trainer.step(*stage)
+        loss_host[0:1].copy_(loss.reshape(1), non_blocking=True)
+        loss_host[1:3].copy_(mse, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                     # the driver loop reads loss.item() each iter
+
+    for s in range(2):
+        step_e2e(s)
+    ms_e2e = timed(step_e2e, K)
+
+    total_rays = n_rays * world
+    value = total_rays * K / (ms_total * 1e-3)
+    e2e = total_rays * K / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    pk, pk_kind = peaks()
+    flops_step = mlp_flops_per_step(cfg, n_rays)
+    tf_achieved = flops_step * K / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
+    peak_tf = pk["bf16_tflops_sustained"]
+    line = {
+        "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.mlp_mode == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": desc, "rays_per_gpu": n_rays, "mlp_mode": args.mlp_mode,
+                   "l2": "per-step working set (activations + workspaces, GBs) far exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": tf_achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (tf_achieved / peak_tf) if tf_achieved else None, "traffic": None,
+                     "kernel": "NeRF MLP fwd+bwd (K1), %d calls/step" % (mlp_calls // max(K, 1)),
+                     "peak_kind": f"{pk_kind} bf16 sustained (MEASURED_PEAKS.json)",
+                     "mlp_ms_per_step": mlp_ms / K if K else None},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = min(args.cpu_rays, n_rays)
+        rps, sec, threads = cpu_baseline(cfg, kind, n_cpu, 2, 1)
+        line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": f"{n_cpu}-ray batch of the workload, fwd+bwd, 1 warm-up + 2 timed steps, "
+                                          "torch CPU fp32 oracle"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+// Shared helpers for the ddnerf_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ddnerf_b200.h"
+
+#define DDNERF_EXPORT __attribute__((visibility("default")))
+
+namespace ddnerf {
+
+void set_error(const char* fmt, ...);
+void count_launches(int n);          // bookkeeping for ddnerf_launch_count()
+
+#define DDNERF_CHECK_ARG(cond, ...)              \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::ddnerf::set_error(__VA_ARGS__);    \
+            return 1;                            \
+        }                                        \
+    } while (0)
+
+#define DDNERF_CHECK_LAUNCH(name)                                              \
+    do {                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                  \
+        if (e__ != cudaSuccess) {                                              \
+            ::ddnerf::set_error("%s: %s", name, cudaGetErrorString(e__));      \
+            return 2;                                                          \
+        }                                                                      \
+    } while (0)
+
+// after a successful launch of n kernels
+#define DDNERF_LAUNCHED(name, n)        \
+    do {                                \
+        DDNERF_CHECK_LAUNCH(name);      \
+        ::ddnerf::count_launches(n);    \
+    } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Reductions / scans over a power-of-two lane group of width G (G <= 32) inside a warp.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, G);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_incl_sum(float v, int gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        float n = __shfl_up_sync(FULL, v, o, G);
+        if (gl >= o) v += n;
+    }
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_incl_prod(float v, int gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        float n = __shfl_up_sync(FULL, v, o, G);
+        if (gl >= o) v *= n;
+    }
+    return v;
+}
+// inclusive suffix sum (lane gl gets sum of lanes >= gl)
+template <int G>
+__device__ __forceinline__ float group_suffix_sum(float v, int gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        float n = __shfl_down_sync(FULL, v, o, G);
+        if (gl + o < G) v += n;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// torch.nn.functional.softplus (beta=1, threshold=20)
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float normal_cdff_(float x) {
+    return 0.5f * (1.0f + erff(x / 1.41421354f));      // math_utils.py:193-200, sqrt(2) in fp32
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ddnerf

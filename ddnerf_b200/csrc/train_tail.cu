@@ -1,0 +1,85 @@
+// Training-step tail on device: photometric loss + its gradient, and Adam on the flat bucket.
+//
+// Replaces train_model.py:156-167 (loss = sum_j coef_j * mse(rgb_j, target)) and :175-177
+// (torch.optim.Adam.step over 26 + 24 separate tensors) of the reference.  SURVEY.md section 8f
+// row f2: once the per-ray path is fused, dozens of tiny optimizer launches dominate the step,
+// so parameters live in one flat fp32 bucket that one kernel updates (and one all-reduce sums).
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ddnerf {
+namespace {
+
+__global__ void mse_kernel(const float* __restrict__ rgb0, const float* __restrict__ rgb1, const float* __restrict__ target,
+                           float coef0, float coef1, float* __restrict__ g0, float* __restrict__ g1,
+                           float* __restrict__ mse_out, int64_t n) {
+    __shared__ float red[2][8];
+    float s0 = 0.f, s1 = 0.f;
+    const float inv = 1.0f / (float)n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float tg = __ldg(target + e);
+        float d0 = __ldg(rgb0 + e) - tg;
+        s0 += d0 * d0;
+        if (g0) g0[e] = coef0 * 2.0f * d0 * inv;
+        if (rgb1) {
+            float d1 = __ldg(rgb1 + e) - tg;
+            s1 += d1 * d1;
+            if (g1) g1[e] = coef1 * 2.0f * d1 * inv;
+        }
+    }
+    s0 = group_sum<32>(s0); s1 = group_sum<32>(s1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        atomicAdd(mse_out + threadIdx.x, s * inv);
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float gr = __ldg(g + e) * gscale;
+        float mm = m[e] + (gr - m[e]) * (1.0f - b1);           // exp_avg.lerp_(grad, 1-beta1)
+        float vv = v[e] * b2 + (1.0f - b2) * gr * gr;          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+        m[e] = mm; v[e] = vv;
+        float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] -= (lr / bc1) * (mm / denom);
+    }
+}
+
+}  // namespace
+}  // namespace ddnerf
+
+using namespace ddnerf;
+
+extern "C" DDNERF_EXPORT int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, float coef0, float coef1,
+                               float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N, void* stream) {
+    DDNERF_CHECK_ARG(rgb0 && target && mse_out, "mse_loss: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(mse_out, 0, 2 * sizeof(float), st);
+    if (N == 0) return 0;
+    int64_t n = N * 3;
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 592);
+    mse_kernel<<<blocks, 256, 0, st>>>(rgb0, rgb1, target, coef0, coef1, g_rgb0, g_rgb1, mse_out, n);
+    DDNERF_LAUNCHED("mse_loss", 1);
+    return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+    DDNERF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
+    DDNERF_CHECK_ARG(step >= 1, "adam_step: step=%d must be >= 1", step);
+    if (n == 0) return 0;
+    float bc1 = 1.0f - powf(beta1, (float)step);
+    float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                        eps, bc1, bc2_sqrt, grad_scale);
+    DDNERF_LAUNCHED("adam_step", 1);
+    return 0;
+}

@@ -1,0 +1,206 @@
+"""Mirror of the reference's ``models/models.py``: ``GeneralMipNerfModel`` (mip-NeRF) and
+``DDNerfModel`` with the reference's public surface (``run_iter``, ``predict``, ``run_network``,
+``get_rays_batches``, ``to``, ``load_weights_from_checkpoint``, ``train``, ``eval``, ``.coarse``,
+``.fine``, ``.cfg``) and output-dict contract, on the CUDA operators of this package.
+
+Differences in mechanism (not in results): ``run_network`` makes one fused encode+MLP call per
+ray chunk instead of cast_rays -> IPE -> dir-enc -> cat -> per-minibatch 13-layer loops; the
+samplers / compositor / dp-loss are single kernels.  Random tensors the reference draws inside the
+path can be injected through ``self.randoms`` (dict with any of ``t_rand``, ``noise0``,
+``u_rand``, ``noise1``; consumed per chunk) -- used by the parity tests.
+"""
+import torch
+
+from . import base_architectures
+from .samplers import *  # noqa: F401,F403
+from .samplers import sample_first_cycle, sample_pdf, sample_pdf_with_mu_sigma
+from .dd_utils import estimate_dp_loss
+from ..general_utils.volume_rendering_utils import volume_render_radiance_field
+from ..general_utils.nerf_helpers import get_embedding_function, get_minibatches
+from ..general_utils.math_utils import approximate_cdf, integrated_pos_enc
+
+
+class GeneralMipNerfModel(torch.nn.Module):
+    """models.py:9-184."""
+
+    def __init__(self, cfg, backbone="MipNeRFModel"):
+        super().__init__()
+        self.coarse = getattr(base_architectures, backbone)(
+            hidden_size=cfg.nerf.coarse_hidden_size, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False,
+            include_input_dir=True, use_viewdirs=True)
+        self.fine = self.coarse                                   # models.py:28 shared weights
+        self.encode_position_fn = integrated_pos_enc
+        self.cfg = cfg
+        self.encode_direction_fn = get_embedding_function(num_encoding_functions=4, include_input=True,
+                                                          log_sampling=True)
+        self.randoms = None
+        # models.py:292-300 records boolean-masked (data-dependent length) tensors every pass, which
+        # forces a device sync; a trainer that does not log them can switch this off.
+        self.record_distributions = True
+
+    # ---- orchestration -------------------------------------------------------------------
+    def run_iter(self, ray_origins, ray_directions, ray_rad, mode="train", depth_analysis_validation=False,
+                 rgb_target=None):
+        """models.py:40-73."""
+        shape_rgb = ray_directions.shape
+        shape_depth = ray_directions.shape[:-1]
+        batches = self.get_rays_batches(ray_origins, ray_directions, ray_rad, mode)
+        if rgb_target is not None:
+            rgb_targets = get_minibatches(rgb_target.view((-1, 3)), chunksize=getattr(self.cfg.nerf, mode).chunksize)
+        else:
+            rgb_targets = [None for _ in batches]
+        pred = []
+        offset = 0
+        for batch, tgt in zip(batches, rgb_targets):
+            self._chunk_rows = (offset, offset + batch.shape[0])
+            pred.append(self.predict(batch, mode, depth_analysis_validation, tgt))
+            offset += batch.shape[0]
+        output = pred[0]
+        for i in range(1, len(pred)):
+            for j in range(len(output)):
+                for key in pred[i][j].keys():
+                    if (pred[i][j][key] is not None) and (pred[i][j][key] is not False):
+                        output[j][key] = torch.cat((output[j][key], pred[i][j][key]), dim=0)
+        if mode == "validation" and not depth_analysis_validation:
+            for i in range(len(output)):
+                output[i]["rgb"] = output[i]["rgb"].view(shape_rgb)
+                for k in ("disp", "acc", "depth"):
+                    output[i][k] = output[i][k].view(shape_depth)
+                if output[i].get("corrected_disp_map") is not None:
+                    output[i]["corrected_disp_map"] = output[i]["corrected_disp_map"].view(shape_depth)
+        return output
+
+    def _rnd(self, key):
+        """Injected random tensor for the current ray chunk, or None (= draw like the reference)."""
+        if not self.randoms or self.randoms.get(key) is None:
+            return None
+        lo, hi = getattr(self, "_chunk_rows", (0, None))
+        return self.randoms[key][lo:hi]
+
+    def _mode_cfg(self, mode):
+        return getattr(self.cfg.nerf, mode)
+
+    def predict(self, ray_batch, mode, depth_analysis_validation, rgb_target=None):
+        """models.py:75-114."""
+        if depth_analysis_validation:
+            raise NotImplementedError("depth_analysis_validation plots (math_utils.py:210-278) are out of scope; "
+                                      "run them with the reference implementation")
+        rd = ray_batch[..., 3:6]
+        near, far = ray_batch[..., 7:8], ray_batch[..., 8:9]
+        mcfg = self._mode_cfg(mode)
+        ret = {}
+        t_vals = weights = None
+        for i in range(2):
+            if i == 0:
+                t_vals = sample_first_cycle(self.cfg, near, far, mode, t_rand=self._rnd("t_rand"))
+            else:
+                t_vals = sample_pdf(t_vals, weights, mcfg.num_fine + 1, self.cfg, det=(mcfg.perturb == 0.0),
+                                    rand=self._rnd("u_rand")).detach()
+            radiance_field = self.run_network(ray_batch, t_vals, self.coarse, mode)
+            rgb, disp, acc, weights, depth, _, _ = volume_render_radiance_field(
+                radiance_field, t_vals, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
+                white_background=mcfg.white_background, cfg=self.cfg, noise=self._rnd(f"noise{i}"), want_rgb=False)
+            ret[i] = {"rgb": rgb, "disp": disp, "acc": acc, "weights": weights, "depth": depth}
+        return ret
+
+    def run_network(self, ray_batch, t_vals, network, mode):
+        """models.py:117-142: [N,12] rays + [N,S+1] fence-posts -> [N,S,C] raw radiance field."""
+        return network.forward_rays(ray_batch, t_vals, self.cfg.nerf.ray_shape)
+
+    def get_rays_batches(self, ray_origins, ray_directions, ray_rad, mode):
+        """models.py:144-162."""
+        viewdirs = ray_directions / ray_directions.norm(p=2, dim=-1).unsqueeze(-1)
+        viewdirs = viewdirs.view((-1, 3))
+        ro = ray_origins.view((-1, 3))
+        rd = ray_directions.reshape((-1, 3))
+        ray_rad = ray_rad.reshape((-1, 1))
+        near = self.cfg.dataset.near * torch.ones_like(rd[..., :1])
+        far = self.cfg.dataset.far * torch.ones_like(rd[..., :1])
+        rays = torch.cat((ro, rd, ray_rad, near, far, viewdirs), dim=-1)
+        return get_minibatches(rays, chunksize=getattr(self.cfg.nerf, mode).chunksize)
+
+    # ---- nn.Module plumbing the drivers rely on (models.py:164-184) -----------------------
+    def to(self, device):
+        self.coarse.to(device)
+        self.fine.to(device)
+
+    def load_weights_from_checkpoint(self, checkpoint):
+        self.coarse.load_state_dict(checkpoint["model_1_state_dict"])
+        if self.cfg.nerf.type != "GeneralMipNerfModel":
+            self.fine.load_state_dict(checkpoint["model_2_state_dict"])
+
+    def train(self, mode=True):
+        self.coarse.train(mode)
+        self.fine.train(mode)
+
+    def eval(self):
+        self.coarse.eval()
+        self.fine.eval()
+
+
+class DDNerfModel(GeneralMipNerfModel):
+    """models.py:187-322."""
+
+    def __init__(self, cfg):
+        GeneralMipNerfModel.__init__(self, cfg, backbone="DepthMipNeRFModel")
+        try:
+            hidden_size_fine = cfg.nerf.fine_hidden_size
+        except Exception:
+            print("no nidden size params for fine model, set 256")
+            hidden_size_fine = 256
+        self.fine = base_architectures.MipNeRFModel(
+            hidden_size=hidden_size_fine, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False,
+            include_input_dir=True, use_viewdirs=True)
+
+    def predict(self, ray_batch, mode, depth_analysis_validation, rgb_target=None):
+        if depth_analysis_validation:
+            raise NotImplementedError("depth_analysis_validation plots (math_utils.py:210-278) are out of scope; "
+                                      "run them with the reference implementation")
+        rd = ray_batch[..., 3:6]
+        near, far = ray_batch[..., 7:8], ray_batch[..., 8:9]
+        mcfg = self._mode_cfg(mode)
+        tp = self.cfg.train_params
+        ret = {}
+
+        # ---- pass 0: coarse network with the depth-distribution head (models.py:222-273)
+        t0 = sample_first_cycle(self.cfg, near, far, mode, t_rand=self._rnd("t_rand"))
+        rf0 = self.run_network(ray_batch, t0, self.coarse, mode)
+        raw_mus, raw_sigmas = rf0[:, :, -2], rf0[:, :, -1]
+        mus = torch.sigmoid(raw_mus)
+        sigmas = torch.sigmoid(raw_sigmas) + 0.001
+        sig_loss = (torch.abs(raw_sigmas) ** 2).sum() / raw_sigmas.shape[0]
+        mus_loss = (torch.abs(raw_mus) ** 2).sum() / raw_mus.shape[0]
+        mus_reg = tp.dist_reg_coeficient * mus_loss
+        sig_reg = tp.dist_reg_coeficient * sig_loss
+        left_tail = approximate_cdf((0 - mus) / sigmas)
+        part_inside = approximate_cdf((1 - mus) / sigmas) - left_tail
+        rgb, disp, acc, w0, depth, cdisp, _ = volume_render_radiance_field(
+            rf0[:, :, :-2], t0, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
+            white_background=mcfg.white_background, mus=mus, cfg=self.cfg, noise=self._rnd("noise0"), want_rgb=False)
+        smoothed_sigmas = sigmas * tp.gaussian_smooth_factor
+        smoothed_left_tail = approximate_cdf((0 - mus) / smoothed_sigmas)
+        smoothed_part_inside = approximate_cdf((1 - mus) / smoothed_sigmas) - smoothed_left_tail
+        rec = {}
+        if self.record_distributions:                           # models.py:292-300 (mask from pass 0)
+            sel = (w0 / torch.sum(w0, dim=-1, keepdim=True)) > 0.1
+            rec = {"mus": mus[sel], "sigmas": sigmas[sel], "smoothed_sigmas": smoothed_sigmas[sel]}
+        else:
+            rec = {"mus": None, "sigmas": None, "smoothed_sigmas": None}
+        ret[0] = {"rgb": rgb, "disp": disp, "acc": acc, "weights": w0, "depth": depth, **rec, "dp_loss": None,
+                  "corrected_disp_map": cdisp, "mus_loss": mus_loss.unsqueeze(0), "sig_loss": sig_loss.unsqueeze(0),
+                  "mus_reg": mus_reg.unsqueeze(0), "sig_reg": sig_reg.unsqueeze(0)}
+
+        # ---- pass 1: fine network on depth-distribution samples (models.py:225-237, 276-289)
+        t1 = sample_pdf_with_mu_sigma(t0, w0, mus, smoothed_sigmas, smoothed_part_inside, smoothed_left_tail,
+                                      mcfg.num_fine + 1, self.cfg, det=(mcfg.perturb == 0.0),
+                                      rand=self._rnd("u_rand")).detach()
+        rf1 = self.run_network(ray_batch, t1, self.fine, mode)
+        rgb1, disp1, acc1, w1, depth1, _, _ = volume_render_radiance_field(
+            rf1, t1, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
+            white_background=mcfg.white_background, mus=None, cfg=self.cfg, noise=self._rnd("noise1"), want_rgb=False)
+        dp_loss = estimate_dp_loss(t1, t0, w1.detach(), w0, mus, sigmas, left_tail.detach(), part_inside.detach(),
+                                   self.cfg) * (t1.shape[1] - 1)
+        dp_loss = (dp_loss + mus_reg + sig_reg).unsqueeze(0)
+        ret[1] = {"rgb": rgb1, "disp": disp1, "acc": acc1, "weights": w1, "depth": depth1, **rec, "dp_loss": dp_loss,
+                  "corrected_disp_map": None}
+        return ret

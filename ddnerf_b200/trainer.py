@@ -1,0 +1,111 @@
+"""One training step of the reference's loop (train_model.py:132-177) on the CUDA path, with the
+data-parallel extension of SURVEY.md section 8e.
+
+The reference keeps 26 (+24) parameter tensors and steps two ``torch.optim.Adam`` objects over
+them tensor by tensor.  Here each network's parameters are views into ONE flat fp32 bucket; the
+gradients are gathered into a matching flat bucket, summed across ranks with a single NCCL
+all-reduce (rays shard across ranks, weights are replicated) and applied by one fused Adam kernel.
+The per-parameter ``nn.Parameter`` objects (names, shapes, ``state_dict``) stay what the
+reference's checkpoints expect.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
+    """general_utils/nerf_helpers.py:211-245."""
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    else:
+        delay_rate = 1.0
+    t = min(max(step / max_steps, 0), 1)
+    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+class FlatBucket:
+    """All parameters of one network as views into one contiguous fp32 buffer + Adam state."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters()]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            off += n
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step = 0
+
+    def gather_grads(self):
+        """Copy the per-parameter .grad tensors into the flat gradient bucket (one cat kernel)."""
+        torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params],
+                  out=self.grad)
+        for p in self.params:
+            p.grad = None
+
+    def adam(self, lr, grad_scale=1.0):
+        self.step += 1
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step, grad_scale=grad_scale)
+
+
+class Trainer:
+    """Drives ``model.run_iter`` + loss + backward + (all-reduce) + Adam, one call per iteration."""
+
+    def __init__(self, model, train_iters=200001, distributed=None):
+        self.model = model
+        self.cfg = model.cfg
+        self.is_dd = self.cfg.nerf.type == "DDNerfModel"
+        self.buckets = [FlatBucket(model.coarse)]
+        if self.is_dd:                                          # train_model.py:93-98 second optimizer
+            self.buckets.append(FlatBucket(model.fine))
+        self.train_iters = train_iters
+        self.iter = 0
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size() if self.distributed else 1
+        tp = self.cfg.train_params
+        self._smooth0 = tp.gaussian_smooth_factor
+        self._dsmooth = (tp.gaussian_smooth_factor - tp.final_smooth) / tp.finnish_smooth
+        model.record_distributions = False
+
+    def lr(self, i):
+        return learning_rate_decay(i, 0.0005, 5e-6, self.train_iters, lr_delay_steps=2500, lr_delay_mult=0.01)
+
+    def step(self, ray_origins, ray_directions, ray_rad, target):
+        """train_model.py:135-177 for one iteration.  Returns (loss, mse[2]) as device tensors (no
+        host sync)."""
+        i, tp = self.iter, self.cfg.train_params
+        if i < tp.finnish_smooth:                                # train_model.py:135-138
+            tp.gaussian_smooth_factor = self._smooth0 - self._dsmooth * i
+        else:
+            tp.gaussian_smooth_factor = tp.final_smooth
+        if i == tp.max_pdf_pad_iters:
+            tp.pdf_padding = False
+        self.model.train()
+        out = self.model.run_iter(ray_origins, ray_directions, ray_rad, mode="train", rgb_target=target)
+        coef = tp.loss_coeficients
+        mse, g0, g1 = ops.mse_loss_and_grad(out[0]["rgb"], out[1]["rgb"], target, coef[0], coef[1])
+        loss = coef[0] * mse[0] + coef[1] * mse[1]
+        tensors, grads = [out[0]["rgb"], out[1]["rgb"]], [g0, g1]
+        if self.is_dd:                                           # train_model.py:163-167
+            dp = out[1]["dp_loss"].mean()
+            loss = loss + tp.dp_coeficient * dp.detach()
+            tensors.append(dp)
+            grads.append(torch.full_like(dp, tp.dp_coeficient))
+        torch.autograd.backward(tensors, grads)
+        lr = self.lr(i)
+        for b in self.buckets:
+            b.gather_grads()
+            if self.distributed and self.world > 1:
+                dist.all_reduce(b.grad, op=dist.ReduceOp.SUM)
+            b.adam(lr, grad_scale=1.0 / self.world)
+        self.iter += 1
+        return loss, mse

@@ -1,0 +1,151 @@
+/*
+ * ddnerf_b200 -- C ABI of the B200-native DDNeRF / mip-NeRF per-ray hot path.
+ *
+ * The reference (dadonda89/DDNeRF) is pure Python/PyTorch and has no FFI; each entry point
+ * below replaces one of its Python functions (cited as file:line of the reference) and is what
+ * a Python binding (ctypes) of that function calls.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (nothing is allocated or freed
+ *     here); outputs are pre-sized by the caller; fp32 row-major unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync;
+ *   - return value 0 = ok, non-zero = error, message via ddnerf_last_error() (thread-local);
+ *   - N = rays, S = samples (intervals) of the current pass, fence-posts t[N, S+1].
+ */
+#ifndef DDNERF_B200_H_
+#define DDNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDNERF_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------- */
+int         ddnerf_version(void);
+const char* ddnerf_last_error(void);
+/* 1 when the running device is compute capability 10.x (tcgen05 path usable). */
+int         ddnerf_device_is_sm100(void);
+/* Number of kernels this library has launched in the calling process (monotonic). */
+int64_t     ddnerf_launch_count(void);
+
+/* ---- K3: samplers ---------------------------------------------------------------------- */
+/* sample_first_cycle, models/samplers.py:30-62.  near/far: per-ray scalars with element
+ * strides (rays[N,12] columns 7/8 -> stride 12).  t_rand [N,S+1] or NULL (perturb off). */
+int ddnerf_sample_first_cycle(const float* near, const float* far, int64_t ray_stride,
+                              const float* t_rand, float* t_out, int64_t N, int S,
+                              int lindisp, void* stream);
+
+/* sample_pdf, models/samplers.py:64-121 (mip-NeRF inverse-CDF resampling).
+ * bins [N,S+1], weights [N,S], rand [N,n] uniform draws or NULL (det=True), out [N,n];
+ * idx_out [N,n] int32 or NULL receives the interval index j of every sample. */
+int ddnerf_sample_pdf(const float* bins, const float* weights, const float* rand, float* out,
+                      int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, void* stream);
+
+/* sample_pdf_with_mu_sigma, models/samplers.py:124-215 (DDNeRF Gaussian-in-cell resampling,
+ * endpoints pinned to near_cfg/far_cfg, ascending sort). */
+int ddnerf_sample_pdf_mu_sigma(const float* bins, const float* weights, const float* mus,
+                               const float* sigmas, const float* part_inside,
+                               const float* left_tail, const float* rand, float* out,
+                               int32_t* idx_out, int64_t N, int S, int n, int pdf_padding,
+                               float near_cfg, float far_cfg, void* stream);
+
+/* The interval search alone (samplers.py:106-116): idx = #{cdf <= u} - 1, on caller-provided
+ * CDFs.  Used by the bit-exactness test ("identical CDFs -> identical indices"). */
+int ddnerf_find_interval(const float* cdf, const float* u, int32_t* idx_out, int64_t N,
+                         int S, int n, void* stream);
+
+/* ---- K2: encoding ------------------------------------------------------------------------ */
+/* cast_rays + integrated_pos_enc + positional_encoding of run_network,
+ * models/models.py:117-133, general_utils/math_utils.py:7-166, nerf_helpers.py:127-171.
+ * rays [N,12] = (o3,d3,radius,near,far,viewdir3).  Writes the 96 IPE features of sample row
+ * r = ray*S+i to enc_out[r*ld_enc + 0..95] and the 27 view-direction features to
+ * dir_out[r*ld_dir + 0..26].  ray_shape: 0 cone, 1 cylinder. */
+int ddnerf_encode(const float* rays, const float* t_vals, float* enc_out, int64_t ld_enc,
+                  float* dir_out, int64_t ld_dir, int64_t N, int S, int ray_shape, void* stream);
+
+/* ---- K1: the NeRF MLP (models/base_architectures.py:3-126) ------------------------------- */
+/* Parameter table: 13 (weight,bias) pairs in state_dict order
+ *   0..7 layers_xyz.{0..7}, 8 fc_feat, 9 fc_alpha, 10 layers_dir.0, 11 fc_rgb, 12 fc_mu_sigma
+ * (entry 12 NULL for MipNeRFModel).  Weights are nn.Linear layout [out,in], fp32. */
+#define DDNERF_MLP_NPARAMS 13
+typedef struct {
+    const float* w[DDNERF_MLP_NPARAMS];
+    const float* b[DDNERF_MLP_NPARAMS];
+} ddnerf_mlp_params;
+typedef struct {
+    float* w[DDNERF_MLP_NPARAMS];
+    float* b[DDNERF_MLP_NPARAMS];
+} ddnerf_mlp_grads;
+
+/* Bytes of activation workspace the fp32 path needs for `rows` sample rows. */
+int64_t ddnerf_mlp_f32_workspace_bytes(int64_t rows);
+
+/* fp32 forward over rows = N*S samples, features produced in-kernel from rays/t (K2 fused as
+ * producer).  out [rows, C] with C = 4 (rgb,density) or 6 (+raw_mu,raw_sigma).  `workspace`
+ * keeps every layer's activations for the backward pass. */
+int ddnerf_mlp_f32_forward(const ddnerf_mlp_params* p, const float* rays, const float* t_vals,
+                           int64_t N, int S, int ray_shape, int out_channels, float* out,
+                           void* workspace, void* stream);
+/* fp32 forward from a caller-provided feature matrix x [rows,123] (MipNeRFModel.forward). */
+int ddnerf_mlp_f32_forward_x(const ddnerf_mlp_params* p, const float* x, int64_t rows,
+                             int out_channels, float* out, void* workspace, void* stream);
+/* fp32 backward: grad_out [rows,C] -> ACCUMULATES into g (caller zeroes it); dx [rows,123]
+ * or NULL.  `workspace` is the one the matching forward filled. */
+int ddnerf_mlp_f32_backward(const ddnerf_mlp_params* p, const ddnerf_mlp_grads* g,
+                            const float* grad_out, int64_t rows, int out_channels, float* dx,
+                            void* workspace, void* stream);
+
+/* ---- K4: alpha compositing (general_utils/volume_rendering_utils.py:6-84) ---------------- */
+/* raw [N,S,raw_stride] (channels 0..3 = r,g,b,density), t [N,S+1], rd = ray directions with
+ * row stride rd_stride, noise [N,S] unit normal or NULL (density += noise*noise_std),
+ * mus [N,S] or NULL.  Outputs: rgb_map [N,3], disp [N], acc [N], weights [N,S], depth [N],
+ * cdisp [N] (only when mus), rgb [N,S,3] or NULL. */
+int ddnerf_composite_forward(const float* raw, int raw_stride, const float* t, const float* rd,
+                             int64_t rd_stride, const float* noise, float noise_std,
+                             const float* mus, int white_background, int blender,
+                             float* rgb_map, float* disp, float* acc, float* weights,
+                             float* depth, float* cdisp, float* rgb, int64_t N, int S,
+                             void* stream);
+/* Analytic backward.  Cotangents g_* may each be NULL (= zero).  Writes g_raw [N,S,4] and
+ * g_mus [N,S] (when mus and g_mus non-NULL). */
+int ddnerf_composite_backward(const float* raw, int raw_stride, const float* t, const float* rd,
+                              int64_t rd_stride, const float* noise, float noise_std,
+                              const float* mus, int white_background, int blender,
+                              const float* g_rgb_map, const float* g_disp, const float* g_acc,
+                              const float* g_weights, const float* g_depth, const float* g_cdisp,
+                              float* g_raw, float* g_mus, int64_t N, int S, void* stream);
+
+/* ---- K5: depth-distribution loss (models/dd_utils.py:6-78) ------------------------------- */
+/* scratch: >= 4 floats, zeroed by the call.  loss_out: 1 float = kl_div(..., 'mean').
+ * ray_aux [N,2] receives per-ray (Z0, Zq) for the backward. */
+int ddnerf_dp_loss_forward(const float* t1, const float* t0, const float* w1, const float* w0,
+                           const float* mus0, const float* sigmas0, const float* lt0,
+                           const float* pin0, int blender, float* loss_out, float* scratch,
+                           int64_t N, int S0, int S1, void* stream);
+/* g_loss: device pointer to the scalar cotangent.  Writes g_w0, g_mus0, g_sigmas0 [N,S0].
+ * scratch is the buffer the forward filled (holds the relevant-ray count). */
+int ddnerf_dp_loss_backward(const float* t1, const float* t0, const float* w1, const float* w0,
+                            const float* mus0, const float* sigmas0, const float* lt0,
+                            const float* pin0, int blender, const float* g_loss,
+                            const float* scratch, float* g_w0, float* g_mus0, float* g_sigmas0,
+                            int64_t N, int S0, int S1, void* stream);
+
+/* ---- training-step tail on the flat parameter bucket (train_model.py:156-177) ------------ */
+/* loss = sum_j coef_j * mse(rgb_j, target); writes g_rgb_j = coef_j*2*(rgb_j-target)/(3N).
+ * mse_out [2].  rgb1/g_rgb1 may be NULL. */
+int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, float coef0,
+                    float coef1, float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N,
+                    void* stream);
+/* torch.optim.Adam (no weight decay, no amsgrad) on a flat fp32 bucket; grad_scale multiplies
+ * the gradient first (1/world_size after an all-reduce sum). */
+int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, float lr, float beta1, float beta2, float eps, int step,
+                     float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDNERF_B200_H_ */

@@ -1,0 +1,354 @@
+"""GPU suite: the CUDA path (through the C ABI) against the golden vectors made from the reference
+and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path 1e-3 max-abs on sample depths and rendered
+rgb/depth -- the per-kernel checks below are much tighter (1e-5..1e-4) because each kernel
+follows the reference's fp32 arithmetic op by op; search indices are bit-exact given identical
+CDFs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddnerf_oracle as orc
+from tests.conftest import load_golden
+from tests.test_oracle_golden import E2E, e2e_setup
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV) if isinstance(t, torch.Tensor) else t
+
+
+def close(a, b, rtol=1e-5, atol=1e-5):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), rtol=rtol, atol=atol, equal_nan=True)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ddnerf_b200 import ops as _ops
+    return _ops
+
+
+def test_library_on_device(ops):
+    from ddnerf_b200 import _lib
+    lib = _lib.load()
+    assert lib.ddnerf_version() == 1
+    assert lib.ddnerf_device_is_sm100() == 1, "tests must run on a B200 (sm_100)"
+
+
+def test_cpu_tensor_raises(ops):
+    with pytest.raises(RuntimeError):
+        ops.encode(torch.zeros(2, 12), torch.zeros(2, 5))
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 samplers
+# ---------------------------------------------------------------------------------------------
+def test_first_cycle(ops):
+    g = load_golden("first_cycle")
+    near, far = cu(g["near"]), cu(g["far"])
+    close(ops.sample_first_cycle(near, far, 16), g["fc_det_t"].expand(24, 17), 1e-6, 1e-6)
+    close(ops.sample_first_cycle(near, far, 32, False, cu(g["fc_jit_rand"])), g["fc_jit_t"], 1e-6, 1e-6)
+    close(ops.sample_first_cycle(near, far, 8, True, cu(g["fc_lind_rand"])), g["fc_lind_t"], 1e-6, 1e-6)
+    # strided near/far taken straight from a packed [N,12] ray tensor
+    rays = torch.zeros(24, 12, device=DEV)
+    rays[:, 7], rays[:, 8] = 2.0, 6.0
+    close(ops.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], 16), g["fc_det_t"].expand(24, 17), 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize("S", [16, 32, 48])
+@pytest.mark.parametrize("wname", ["uniform", "peaked"])
+@pytest.mark.parametrize("pad", [True, False])
+@pytest.mark.parametrize("det", [True, False])
+def test_resamplers_golden(ops, S, wname, pad, det):
+    g = load_golden(f"resample_S{S}")
+    key = f"{wname}_pad{int(pad)}_det{int(det)}"
+    bins, w = cu(g["bins"]), cu(g["w_" + wname])
+    n = g["mip_" + key].shape[1]
+    rand = None if det else cu(g["mip_" + key + "_rand"])
+    close(ops.sample_pdf(bins, w, n, pad, rand), g["mip_" + key], 1e-5, 2e-5)
+    rand = None if det else cu(g["dd_" + key + "_rand"])
+    s = ops.sample_pdf_mu_sigma(bins, w, cu(g["mus"]), cu(g["sigmas"]), cu(g["pin"]), cu(g["lt"]), n, pad,
+                                float(g["near_cfg"]), float(g["far_cfg"]), rand)
+    # erfinv near its singularities amplifies 1-ulp cdf differences; depths are in [2,6]
+    close(s, g["dd_" + key], 1e-4, 2e-4)
+
+
+def test_resampler_one_cell(ops):
+    g = load_golden("resample_onecell")
+    s = ops.sample_pdf_mu_sigma(cu(g["bins"]), cu(g["w"]), cu(g["mus"]), cu(g["sigmas"]), cu(g["pin"]), cu(g["lt"]), 9,
+                                True, float(g["near_cfg"]), float(g["far_cfg"]))
+    close(s, g["dd"], 1e-4, 2e-4)
+
+
+@pytest.mark.parametrize("N,S,n", [(257, 16, 17), (1000, 64, 65), (513, 128, 129), (64, 1, 9)])
+def test_find_interval_bit_exact(ops, N, S, n):
+    """Same CDF in, same interval index out as the reference's mask search (oracle restatement)."""
+    gen = torch.Generator().manual_seed(N + S)
+    w = torch.rand(N, S, generator=gen) ** 3
+    w[:, S // 3: S // 2] = 0.0                      # empty space -> flat (tied) CDF segments
+    cdf = orc.resampling_cdf(w, pdf_padding=False) if S > 1 else torch.tensor([[0.0, 1.0]]).expand(N, 2).contiguous()
+    u = torch.rand(N, n, generator=gen)
+    u[:, 0], u[:, -1] = 0.0, 1.0
+    u[:, 1] = cdf[:, min(1, S)]                      # exactly on an edge
+    j_ref, _ = orc.find_interval(cdf, u)
+    idx = ops.find_interval(cu(cdf), cu(u))
+    assert torch.equal(idx.cpu().long(), j_ref)
+
+
+def test_resampler_indices_match_oracle(ops):
+    g = load_golden("resample_S32")
+    for wname in ("uniform", "peaked"):
+        w = g["w_" + wname]
+        n = 33
+        s_ref, j_ref = orc.sample_pdf(g["bins"], w, n, True, None)
+        s, j = ops.sample_pdf(cu(g["bins"]), cu(w), n, True, None, return_idx=True)
+        # indices may differ only where u sits within float rounding of a CDF edge (the CUDA CDF is a
+        # warp scan in fp32, the CPU one accumulates in double); samples must agree regardless
+        frac = (j.cpu().long() != j_ref).float().mean().item()
+        assert frac < 0.01
+        close(s, s_ref, 1e-5, 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 encoding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["blender", "ff", "360"])
+@pytest.mark.parametrize("shape", ["cone", "cylinder"])
+def test_encoding(ops, kind, shape):
+    g = load_golden(f"encoding_{kind}")
+    N = g["ro"].shape[0]
+    rays = orc.pack_rays(g["ro"], g["rd"], g["rad"], 0.0, 1.0)
+    x = ops.encode(cu(rays), cu(g["t"]), shape)
+    S = g["t"].shape[1] - 1
+    assert x.shape == (N * S, 123)
+    close(x[:, :96].reshape(N, S, 96), g[f"ipe_{shape}"], 1e-5, 1e-5)
+    close(x[:, 96:].reshape(N, S, 27)[:, 0], g["dir_enc"], 1e-6, 1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 MLP (fp32 mode)
+# ---------------------------------------------------------------------------------------------
+def _module(depth, seed):
+    from ddnerf_b200.models import base_architectures as arch
+    net = (arch.DepthMipNeRFModel if depth else arch.MipNeRFModel)(
+        hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True,
+        use_viewdirs=True)
+    net.load_state_dict(orc.init_mlp_params(depth, seed=seed))
+    return net.to(DEV)
+
+
+@pytest.mark.parametrize("depth", [False, True])
+def test_mlp_f32_golden(ops, depth):
+    g = load_golden("mlp_depth" if depth else "mlp_plain")
+    net = _module(depth, 11 + int(depth))
+    x = cu(g["x"]).requires_grad_(True)
+    y = net(x)
+    close(y, g["y"], 1e-4, 1e-5)
+    y.backward(cu(g["gy"]))
+    for k, p in net.named_parameters():
+        if "g_" + k in g:
+            close(p.grad, g["g_" + k], 1e-3, 1e-4)
+    # dx against the oracle
+    params = {k: v.requires_grad_(False) for k, v in orc.init_mlp_params(depth, seed=11 + int(depth)).items()}
+    xr = g["x"].clone().requires_grad_(True)
+    orc.mlp_forward(params, xr).backward(g["gy"])
+    close(x.grad, xr.grad, 1e-3, 1e-4)
+
+
+def test_mlp_f32_ragged_rows(ops):
+    """rows not a multiple of any tile size; fused encode path == explicit feature path."""
+    net = _module(True, 5)
+    N, S = 37, 7
+    g = torch.Generator().manual_seed(3)
+    from ddnerf_b200.rays import synth_rays
+    ro, rd, rad, near, far = synth_rays("blender", N, seed=5)
+    rays = cu(orc.pack_rays(ro, rd, rad, near, far))
+    t = cu(orc.sample_first_cycle(torch.full((N, 1), near), torch.full((N, 1), far), S, False,
+                                  torch.rand(N, S + 1, generator=g)))
+    y1 = net.forward_rays(rays, t, "cone")
+    y2 = net(ops.encode(rays, t, "cone")).reshape(N, S, 6)
+    close(y1, y2, 1e-6, 1e-6)
+    params = orc.init_mlp_params(True, seed=5)
+    close(y1, orc.run_network(params, rays.cpu(), t.cpu()), 1e-4, 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# K4 compositing
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,std,white,use_mus,blender", [
+    ("blender", 0.0, False, False, True), ("blender_noise_white", 1.0, True, False, True),
+    ("blender_mus", 1.0, False, True, True), ("real_mus", 0.5, False, True, False),
+    ("nocfg", 0.0, False, False, False)])
+def test_composite_golden(ops, tag, std, white, use_mus, blender):
+    g = load_golden("render")
+    raw = cu(g["raw"]).requires_grad_(True)
+    mus = cu(g["mus"]).requires_grad_(True)
+    noise = cu(g[f"{tag}_randn"]) if std > 0 else None
+    outs = ops.composite(raw, cu(g["t"]), cu(g["rd"]), noise, std, mus if use_mus else None, white, blender, True)
+    names = ("rgb_map", "disp", "acc", "weights", "depth", "cdisp", "rgb")
+    loss = 0
+    for nme, o in zip(names, outs):
+        if o is None:
+            assert f"{tag}_{nme}" not in g
+            continue
+        ref = g[f"{tag}_{nme}"]
+        if nme in ("disp", "cdisp"):
+            close(1.0 / o, 1.0 / ref, 1e-4, 1e-5)
+        else:
+            close(o, ref, 1e-4, 1e-6)
+        if f"{tag}_ct_{nme}" in g:
+            loss = loss + (o * cu(g[f"{tag}_ct_{nme}"])).sum()
+    loss.backward()
+    gr, gref = raw.grad.cpu(), g[f"{tag}_g_raw"]
+    # rays with sum(weights) ~ 0 have disp ~ 1e10: compare gradients relative to each ray's scale
+    scale = gref.abs().amax(dim=(1, 2), keepdim=True).clamp(min=1e-6)
+    finite = torch.isfinite(gref)
+    assert torch.equal(torch.isfinite(gr), finite)
+    err = ((gr - gref).abs() / scale)[finite].max().item()
+    assert err < 2e-4, err
+    if use_mus:
+        gm, gmref = mus.grad.cpu(), g[f"{tag}_g_mus"]
+        sc = gmref.abs().amax(dim=1, keepdim=True).clamp(min=1e-6)
+        fin = torch.isfinite(gmref)
+        assert ((gm - gmref).abs() / sc)[fin].max().item() < 2e-4
+
+
+@pytest.mark.parametrize("S", [1, 7, 16, 33, 64, 128, 200, 512])
+def test_composite_shapes_vs_oracle(ops, S):
+    N = 65
+    g = torch.Generator().manual_seed(S)
+    t = torch.sort(torch.rand(N, S + 1, generator=g) * 4 + 2, dim=-1)[0]
+    raw6 = torch.randn(N, S, 6, generator=g) * 2
+    rd = torch.randn(N, 3, generator=g)
+    mus = torch.rand(N, S, generator=g)
+    nz = torch.randn(N, S, generator=g)
+    ref = orc.volume_render(raw6[..., :4], t, rd, nz * 0.7, True, True, mus)
+    out = ops.composite(cu(raw6)[..., :4], cu(t), cu(rd), cu(nz), 0.7, cu(mus), True, True, True)   # strided raw view
+    for o, r, nme in zip(out, ref, ("rgb_map", "disp", "acc", "weights", "depth", "cdisp", "rgb")):
+        if nme in ("disp", "cdisp"):
+            close(1.0 / o, 1.0 / r, 1e-4, 1e-5)
+        else:
+            close(o, r, 1e-4, 2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 depth-distribution loss
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", ["16_16", "32_32", "24_40"])
+@pytest.mark.parametrize("wname", ["uniform", "peaked", "bumpy"])
+@pytest.mark.parametrize("cname", ["blender", "real"])
+def test_dp_loss_golden(ops, shape, wname, cname):
+    g = load_golden(f"dp_loss_{shape}")
+    w0 = cu(g[f"{wname}_w0"]).requires_grad_(True)
+    mus = cu(g[f"{wname}_mus"]).requires_grad_(True)
+    sig = cu(g[f"{wname}_sigmas"]).requires_grad_(True)
+    loss = ops.dp_loss(cu(g[f"{wname}_t1"]), cu(g["t0"]), cu(g[f"{wname}_w1"]), w0, mus, sig, cu(g[f"{wname}_lt"]),
+                       cu(g[f"{wname}_pin"]), cname == "blender")
+    close(loss, g[f"{wname}_{cname}_loss"], 2e-4, 1e-6)
+    if wname == "peaked":
+        return      # gradients there are ~p1/q with q ~ 1e-12: ill-conditioned in the reference itself
+    loss.backward()
+    for got, key in ((w0.grad, "g_w0"), (mus.grad, "g_mus"), (sig.grad, "g_sigmas")):
+        ref = g[f"{wname}_{cname}_{key}"]
+        sc = ref.abs().amax(dim=1, keepdim=True).clamp(min=1e-7)
+        assert ((got.cpu() - ref).abs() / sc).max().item() < 2e-3, key
+
+
+# ---------------------------------------------------------------------------------------------
+# end to end through the reference-facing model API
+# ---------------------------------------------------------------------------------------------
+def _build_model(spec, cfg):
+    from ddnerf_b200.config import make_cfg
+    from ddnerf_b200.models import models as M
+    c = make_cfg(model=spec["model"], dataset_type="blender" if spec["blender"] else "REAL360", near=cfg.near,
+                 far=cfg.far, num_coarse=spec["nc"], num_fine=spec["nf"], pdf_padding=spec["pad"],
+                 gaussian_smooth_factor=spec["smooth"], dist_reg_coeficient=cfg.dist_reg_coeficient)
+    model = getattr(M, spec["model"])(c)
+    is_dd = spec["model"] == "DDNerfModel"
+    model.coarse.load_state_dict(orc.init_mlp_params(is_dd, seed=31))
+    if is_dd:
+        model.fine.load_state_dict(orc.init_mlp_params(False, seed=32))
+    model.to(DEV)
+    return model, c
+
+
+@pytest.mark.parametrize("tag", list(E2E))
+def test_end_to_end_golden(ops, tag):
+    spec, g, cfg, pc, pf, rnd, rays = e2e_setup(tag)
+    model, c = _build_model(spec, cfg)
+    model.randoms = {k: cu(v) for k, v in rnd.items()}
+    N = g["ro"].shape[0]
+    if spec["train"]:
+        model.train()
+        out = model.run_iter(cu(g["ro"]), cu(g["rd"]), cu(g["rad"]), mode="train", rgb_target=cu(g["target"]))
+        target = cu(g["target"])
+        loss = 0
+        for j in range(2):
+            loss = loss + cfg.loss_coeficients[j] * torch.nn.functional.mse_loss(out[j]["rgb"], target)
+        if spec["model"] == "DDNerfModel":
+            loss = loss + cfg.dp_coeficient * out[1]["dp_loss"].mean()
+        loss.backward()
+        close(loss, g["loss"], 1e-4, 1e-5)
+        for prefix, net in (("gc_", model.coarse), ("gf_", model.fine if spec["model"] == "DDNerfModel" else None)):
+            if net is None:
+                continue
+            for k, p in net.named_parameters():
+                ref = g[prefix + k]
+                got = p.grad.cpu()
+                got = got if got.numel() <= 4096 else got.flatten()[::97]
+                sc = ref.abs().max().clamp(min=1e-8)
+                assert ((got - ref).abs().max() / sc).item() < 5e-3, (k, ((got - ref).abs().max() / sc).item())
+    else:
+        model.eval()
+        with torch.no_grad():
+            out = model.run_iter(cu(g["ro"]).view(N // 8, 8, 3), cu(g["rd"]).view(N // 8, 8, 3),
+                                 cu(g["rad"]).view(N // 8, 8, 1), mode="validation")
+    for j in range(2):
+        for k in ("rgb", "acc", "weights", "depth", "dp_loss", "mus_loss", "sig_loss"):
+            key = f"out{j}_{k}"
+            if key in g:
+                close(out[j][k].reshape(g[key].shape), g[key], 1e-3, 1e-3)      # BASELINE.json fp32 budget
+                close(out[j][k].reshape(g[key].shape), g[key], 2e-4, 2e-4)      # what we actually hold
+        for k in ("disp", "corrected_disp_map"):
+            key = f"out{j}_{k}"
+            if key in g:
+                close(1.0 / out[j][k].reshape(g[key].shape), 1.0 / g[key], 2e-4, 2e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json cfg2: 4096 rays x 128+128 samples)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(ops):
+    from ddnerf_b200.rays import synth_rays
+    N, S = 4096, 128
+    ro, rd, rad, near, far = synth_rays("blender", N, seed=1)
+    rays = cu(orc.pack_rays(ro, rd, rad, near, far))
+    g = torch.Generator(device=DEV).manual_seed(0)
+    t0 = ops.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], S, False, torch.rand(N, S + 1, device=DEV, generator=g))
+    assert (t0[:, 1:] >= t0[:, :-1]).all() and (t0[:, 0] == near).all() and (t0[:, -1] == far).all()
+    raw = torch.randn(N, S, 4, device=DEV, generator=g) * 3
+    rgb, disp, acc, w, depth, _, _ = ops.composite(raw, t0, rays[:, 3:6], None, 0.0, None, False, True, False)
+    assert (w >= 0).all() and (acc <= 1 + 1e-5).all()
+    assert (rgb >= -0.0011).all() and (rgb <= 1.0011).all()
+    assert ((depth >= near - 1e-4) & (depth <= far + 1e-4)).all()
+    t1 = ops.sample_pdf(t0, w, S + 1, True, torch.rand(N, S + 1, device=DEV, generator=g))
+    assert (t1[:, 1:] >= t1[:, :-1]).all() and (t1 >= near).all() and (t1 <= far).all()
+    mus = torch.rand(N, S, device=DEV, generator=g)
+    sig = torch.rand(N, S, device=DEV, generator=g) * 0.5 + 1e-3
+    lt = 0.5 * (1 + torch.erf((0 - mus) / sig / 2 ** 0.5))
+    pin = 0.5 * (1 + torch.erf((1 - mus) / sig / 2 ** 0.5)) - lt
+    t2 = ops.sample_pdf_mu_sigma(t0, w, mus, sig, pin, lt, S + 1, False, near, far,
+                                 torch.rand(N, S + 1, device=DEV, generator=g))
+    assert (t2[:, 1:] >= t2[:, :-1]).all() and (t2[:, 0] == near).all() and (t2[:, -1] == far).all()
+    # linearity of the compositor in its cotangent: bwd(2g) == 2 bwd(g)
+    rawg = raw.clone().requires_grad_(True)
+    o = ops.composite(rawg, t0, rays[:, 3:6], None, 0.0, None, False, True, False)
+    ct = torch.randn(N, 3, device=DEV, generator=g)
+    (g1,) = torch.autograd.grad((o[0] * ct).sum(), rawg, retain_graph=True)
+    (g2,) = torch.autograd.grad((o[0] * ct * 2).sum(), rawg)
+    close(g2, 2 * g1, 1e-6, 1e-9)
