@@ -55,6 +55,19 @@ __device__ __forceinline__ float group_incl_sum(float v, int gl) {
     }
     return v;
 }
+// Inclusive sum in double.  Used for CDFs: a parallel fp32 scan associates differently per lane, so
+// prefixes that should be equal (increments below 1 ulp, i.e. empty space) can differ by an ulp or even
+// decrease; accumulating in double and rounding once keeps the CDF monotone with exact ties -- and is
+// what the reference's torch.cumsum does on the CPU (it accumulates float tensors in double).
+template <int G>
+__device__ __forceinline__ double group_incl_sum_d(double v, int gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        double n = __shfl_up_sync(FULL, v, o, G);
+        if (gl >= o) v += n;
+    }
+    return v;
+}
 template <int G>
 __device__ __forceinline__ float group_incl_prod(float v, int gl) {
 #pragma unroll

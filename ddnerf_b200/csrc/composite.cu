@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
         if (a.white) Ga -= Gr + Gg + Gb;
         float gdep = gr.g_depth ? __ldg(gr.g_depth + ray) : 0.f;
         if (a.mus) Gc = gdep; else Gd = gdep;
-        if (gr.g_disp) {
+        if (gr.g_disp) {                                       // NaN (0/0, empty non-blender ray) propagates like torch
             float x = d0 / W;
-            if (x > 1e-10f) { float k = -__ldg(gr.g_disp + ray) / (x * x); Gd += k / W; Ga += -k * d0 / (W * W); }
+            if (x > 1e-10f || x != x) { float k = -__ldg(gr.g_disp + ray) / (x * x); Gd += k / W; Ga += -k * d0 / (W * W); }
         }
         if (a.mus && gr.g_cdisp) {
             float x = cd / W;
-            if (x > 1e-10f) { float k = -__ldg(gr.g_cdisp + ray) / (x * x); Gc += k / W; Ga += -k * cd / (W * W); }
+            if (x > 1e-10f || x != x) { float k = -__ldg(gr.g_cdisp + ray) / (x * x); Gc += k / W; Ga += -k * cd / (W * W); }
         }
     }
     // phase 2: walk the chunks backwards with the suffix sum A_i = sum_{k>i} g_k w_k

@@ -77,13 +77,14 @@ __device__ RayState ray_forward(const DpArgs& a, const Smem& sm, int64_t ray, in
     __syncwarp();
     for (int i = lane; i < S0; i += 32) sm.p0[i] = sm.p0[i] / rs.Z0;
     __syncwarp();
-    float carry = 0.f;
+    double carry = 0.0;
     for (int base = 0; base < S0 - 1; base += 32) {            // cdf[m] = min(1, sum_{i<m} p0_i), m=1..S0-1
         int i = base + lane;
         float v = i < S0 - 1 ? sm.p0[i] : 0.f;
-        float incl = group_incl_sum<32>(v, lane) + carry;
+        double incl_d = group_incl_sum_d<32>((double)v, lane) + carry;
+        float incl = (float)incl_d;
         if (i < S0 - 1) { sm.cum[i + 1] = incl; sm.cdf[i + 1] = fminf(1.0f, incl); }
-        carry = __shfl_sync(FULL, incl, 31);
+        carry = __shfl_sync(FULL, incl_d, 31);
     }
     if (lane == 0) { sm.cdf[0] = 0.f; sm.cum[0] = 0.f; sm.cdf[S0] = 1.f; sm.cum[S0] = 2.f; }
     __syncwarp();

@@ -66,12 +66,12 @@ __device__ void build_cdf(const float* __restrict__ w_row, float* wpad, float* w
     }
     const float total = warp_sum(part);
     __syncwarp();
-    float carry = 0.f;
+    double carry = 0.0;
     for (int base = 0; base < S - 1; base += 32) {
         int i = base + lane;
         float v = i < S - 1 ? what[i] / total : 0.f;
-        float incl = group_incl_sum<32>(v, lane) + carry;
-        if (i < S - 1) cdf[i + 1] = fminf(1.0f, incl);
+        double incl = group_incl_sum_d<32>((double)v, lane) + carry;
+        if (i < S - 1) cdf[i + 1] = fminf(1.0f, (float)incl);
         carry = __shfl_sync(FULL, incl, 31);
     }
     if (lane == 0) { cdf[0] = 0.f; cdf[S] = 1.f; }
