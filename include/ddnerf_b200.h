@@ -98,6 +98,15 @@ int ddnerf_mlp_f32_backward(const ddnerf_mlp_params* p, const ddnerf_mlp_grads* 
                             const float* grad_out, int64_t rows, int out_channels, float* dx,
                             void* workspace, void* stream);
 
+/* Descriptor self-test of the tcgen05 path (test infrastructure of the bf16 MLP): one CTA computes
+ * D[128,N] = A.B^T from two operand tile images given in their shared-memory byte layout, with the
+ * shared-memory descriptors (start address 0), instruction descriptor and per-k16-step address
+ * stepping {a_step, a_steps_per_block, a_block_pitch, b_step, b_steps_per_block, b_block_pitch}
+ * supplied by the caller. */
+int ddnerf_tc_gemm_selftest(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
+                            float* d_out, int N, int nk16, uint64_t a_desc, uint64_t b_desc,
+                            uint32_t idesc, const uint32_t* stepping, void* stream);
+
 /* ---- K4: alpha compositing (general_utils/volume_rendering_utils.py:6-84) ---------------- */
 /* raw [N,S,raw_stride] (channels 0..3 = r,g,b,density), t [N,S+1], rd = ray directions with
  * row stride rd_stride, noise [N,S] unit normal or NULL (density += noise*noise_std),
