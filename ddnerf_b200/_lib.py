@@ -36,6 +36,15 @@ SIGNATURES = {
     "ddnerf_mlp_f32_forward": (c_i, [ctypes.POINTER(MlpPtrs), c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p, c_p]),
     "ddnerf_mlp_f32_forward_x": (c_i, [ctypes.POINTER(MlpPtrs), c_p, c_l, c_i, c_p, c_p, c_p]),
     "ddnerf_mlp_f32_backward": (c_i, [ctypes.POINTER(MlpPtrs), ctypes.POINTER(MlpPtrs), c_p, c_l, c_i, c_p, c_p, c_p]),
+    "ddnerf_mlp_tc_wimg_bytes": (c_l, []),
+    "ddnerf_mlp_tc_bias_floats": (c_l, []),
+    "ddnerf_mlp_tc_items": (c_l, [c_l]),
+    "ddnerf_mlp_tc_enc_bytes": (c_l, [c_l]),
+    "ddnerf_mlp_tc_act_save_bytes": (c_l, [c_l]),
+    "ddnerf_mlp_tc_mask_save_bytes": (c_l, [c_l]),
+    "ddnerf_mlp_tc_pack": (c_i, [ctypes.POINTER(MlpPtrs), c_i, c_p, c_p, c_p]),
+    "ddnerf_mlp_tc_encode": (c_i, [c_p, c_p, c_l, c_i, c_i, c_p, c_p]),
+    "ddnerf_mlp_tc_forward": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
     "ddnerf_tc_gemm_selftest": (c_i, [c_p, c_l, c_p, c_l, c_p, c_i, c_i, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                       ctypes.POINTER(ctypes.c_uint32), c_p]),
     "ddnerf_composite_forward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 7 + [c_l, c_i, c_p]),

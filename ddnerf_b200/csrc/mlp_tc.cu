@@ -1,0 +1,567 @@
+// K1 (bf16 throughput mode): the NeRF MLP of models/base_architectures.py:3-126 as ONE persistent,
+// warp-specialised tcgen05 kernel per pass.  A CTA owns a 256-row work item (two 128-row tiles);
+// all 11 GEMMs of the network run back to back with the activations resident on chip:
+//
+//   producer warp  : walks the static load program, streaming 16 KB weight stages (and the encoded
+//                    xyz / view-direction blocks) from L2 into a 6-slot shared-memory ring with
+//                    bulk async copies (TMA engine) completing on mbarriers;
+//   MMA warp       : one thread issues tcgen05.mma (M=128, N=256/144/16, K=16, bf16 -> fp32 in
+//                    TMEM); the two tiles share every weight stage and are interleaved half a layer
+//                    apart so that one tile's epilogue overlaps the other tile's MMAs;
+//   8 epilogue warps: tcgen05.ld the accumulator, add bias, ReLU, convert to bf16 and write the next
+//                    layer's A operand in place (K-major SWIZZLE_128B); density / colour / (mu, sigma)
+//                    heads are extra columns of the last two GEMMs and leave as fp32.
+//
+// The skip connection cat(xyz, h) of layer 5 and the cat(feat, dirs) of the view branch are extra
+// K-chunks of the same accumulation whose A operand is the encoded block in the ring.  In training
+// the epilogues also store every layer's bf16 activations (tile images, bulk stores) and ReLU sign
+// bitmasks for the backward kernels.
+#include <algorithm>
+#include <mutex>
+
+#define DDNERF_TC_WATCHDOG 1
+
+#include "encode.cuh"
+#include "mlp_tc.cuh"
+
+namespace ddnerf {
+namespace {
+
+using namespace tcmlp;
+
+__constant__ Program c_prog_fwd;
+__constant__ PackTable c_pack_fwd;
+
+struct ChainArgs {
+    const uint8_t* wimg;      // packed weight stages (program order)
+    const float* bias;        // packed fp32 biases, [n_epis][256]
+    const uint8_t* enc;       // encoded-feature images, [n_items][64 KB]
+    float* out;               // [rows, C]
+    uint8_t* act_save;        // [layers][n_tiles][64 KB] or null
+    uint32_t* mask_save;      // [layers][n_tiles][128][8] or null
+    int64_t rows;
+    int n_items, C;
+};
+
+struct __align__(16) SmemCtl {
+    uint64_t full[kSlots], empty[kSlots], acc_full[2], act_ready[2];
+    uint32_t tmem_base, pad[3];
+    float bias[2][256];
+};
+constexpr int kSmemBytes = 2 * kActBytes + kSlots * kSlotBytes + (int)sizeof(SmemCtl);
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---- epilogue pieces ------------------------------------------------------------------------
+// 32 accumulator columns [c0, c0+32) of this thread's row: + bias, optional ReLU, -> bf16, stored as
+// four 16-byte chunks of the act buffer.  Returns the sign bitmask (bit i = value i > 0).
+__device__ __forceinline__ uint32_t epi_chunk32(uint32_t tmem_addr, const float* __restrict__ bias_s, int c0, bool relu,
+                                                uint32_t act_u32, int row) {
+    uint32_t v[32];
+    tc::tmem_ld32(tmem_addr + c0, v);
+    tc::tmem_ld_wait();
+    uint32_t pk[16];
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+        float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
+        float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
+        m |= (x0 > 0.f ? 1u : 0u) << i;
+        m |= (x1 > 0.f ? 1u : 0u) << (i + 1);
+        m |= (x2 > 0.f ? 1u : 0u) << (i + 2);
+        m |= (x3 > 0.f ? 1u : 0u) << (i + 3);
+        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+        pk[i / 2] = tc::pack_bf16(x0, x1);
+        pk[i / 2 + 1] = tc::pack_bf16(x2, x3);
+    }
+    const uint32_t base = act_u32 + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)row * 128u;
+    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_shared_v4(base + ((((ch0 + i) ^ (uint32_t)row) & 7u) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    return m;
+}
+
+__device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+    const int T = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
+    const uint32_t tmem_row = ctl->tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
+    float* bias_s = ctl->bias[T];
+    const int bar_id = 1 + T;
+    const int n_tiles = g.n_items * 2;
+    const int n_epis = c_prog_fwd.n_epis;
+    uint32_t acc_phase = 0;
+    bool store_pending = false;
+
+    {   // bias of the first epilogue
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(g.bias + c_prog_fwd.epis[0].bias_off) + row);
+        bias_s[2 * row] = b0.x;
+        bias_s[2 * row + 1] = b0.y;
+        named_bar(bar_id, 128);
+    }
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int tile_g = item * 2 + T;
+        const int64_t row_g = (int64_t)tile_g * 128 + row;
+        for (int e = 0; e < n_epis; ++e) {
+            const Epi E = c_prog_fwd.epis[e];
+            const int en = (e + 1 == n_epis) ? 0 : e + 1;
+            const float2 nb = __ldg(reinterpret_cast<const float2*>(g.bias + c_prog_fwd.epis[en].bias_off) + row);
+            tc::mbar_wait(&ctl->acc_full[T], acc_phase);
+            acc_phase ^= 1;
+            tc::tc_fence_after_sync();
+            if (g.act_save) {            // the previous bulk store of this act buffer must have read it
+                if (row == 0 && store_pending) { tc::bulk_wait_read<0>(); store_pending = false; }
+                named_bar(bar_id, 128);
+            }
+            if (E.mode == EPI_ACT || E.mode == EPI_DIR) {
+                uint32_t mk[8];
+                const int nc = (E.mode == EPI_DIR) ? 128 : 256;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    mk[c] = 0;
+                    if (c * 32 < nc) mk[c] = epi_chunk32(tmem_row, bias_s, c * 32, E.relu != 0, act_u32, row);
+                }
+                if (E.mode == EPI_DIR) {                         // column 128 = density (fc_alpha)
+                    uint32_t v[16];
+                    tc::tmem_ld16(tmem_row + 128, v);
+                    tc::tmem_ld_wait();
+                    if (row_g < g.rows) g.out[row_g * g.C + 3] = __uint_as_float(v[0]) + bias_s[128];
+                }
+                if (g.mask_save && E.save_layer >= 0 && E.relu) {
+                    uint4* mp = reinterpret_cast<uint4*>(g.mask_save + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8);
+                    mp[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+                    mp[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
+                }
+            } else {                                             // EPI_OUT: colour (+ mu, sigma) heads
+                uint32_t v[16];
+                tc::tmem_ld16(tmem_row, v);
+                tc::tmem_ld_wait();
+                if (row_g < g.rows) {
+                    float* o = g.out + row_g * g.C;
+                    o[0] = __uint_as_float(v[0]) + bias_s[0];
+                    o[1] = __uint_as_float(v[1]) + bias_s[1];
+                    o[2] = __uint_as_float(v[2]) + bias_s[2];
+                    if (g.C == 6) {
+                        o[4] = __uint_as_float(v[3]) + bias_s[3];
+                        o[5] = __uint_as_float(v[4]) + bias_s[4];
+                    }
+                }
+            }
+            tc::tc_fence_before_sync();          // TMEM reads done before the MMA warp may overwrite D
+            tc::fence_proxy_async_smem();        // act writes visible to tcgen05.mma / bulk store
+            named_bar(bar_id, 128);
+            if (row == 0) {
+                tc::mbar_arrive(&ctl->act_ready[T]);
+                if (g.act_save && E.save_layer >= 0) {
+                    tc::bulk_s2g(g.act_save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
+                                 E.save_bytes);
+                    tc::bulk_commit();
+                    store_pending = true;
+                }
+            }
+            bias_s[2 * row] = nb.x;
+            bias_s[2 * row + 1] = nb.y;
+            named_bar(bar_id, 128);
+        }
+    }
+    if (row == 0) tc::bulk_wait_all<0>();
+}
+
+__device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
+    uint32_t seq = 0;
+    const int n_loads = c_prog_fwd.n_loads;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const uint8_t* enc = g.enc + (size_t)item * kEncItemBytes;
+        for (int i = 0; i < n_loads; ++i, ++seq) {
+            const Load L = c_prog_fwd.loads[i];
+            const uint32_t slot = seq % kSlots, phase = (seq / kSlots) & 1;
+            tc::mbar_wait(&ctl->empty[slot], phase ^ 1);
+            const uint8_t* src = (L.kind == LOAD_W ? g.wimg : enc) + L.off;
+            tc::mbar_expect_tx(&ctl->full[slot], L.bytes);
+            tc::bulk_g2s(ring + slot * kSlotBytes, src, L.bytes, &ctl->full[slot]);
+        }
+    }
+}
+
+__device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, uint8_t* ring) {
+    const uint32_t act_u32 = tc::smem_u32(act_all), ring_u32 = tc::smem_u32(ring);
+    constexpr uint64_t kDesc128 = tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128);
+    constexpr uint64_t kDesc64 = tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64);
+    const uint32_t idesc[3] = {tc::idesc_bf16(128, 256, 0, 0), tc::idesc_bf16(128, 144, 0, 0), tc::idesc_bf16(128, 16, 0, 0)};
+    const uint32_t tmem = ctl->tmem_base;
+    const int n_mmas = c_prog_fwd.n_mmas, n_loads = c_prog_fwd.n_loads;
+    uint32_t base = 0, ready = 0, act_phase0 = 0, act_phase1 = 0;
+    bool first_item = true;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        for (int i = 0; i < n_mmas; ++i) {
+            const Mma op = c_prog_fwd.mmas[i];
+            if ((op.flags & F_WAIT_ACT) || ((op.flags & F_WAIT_PREV) && !first_item)) {
+                if (op.tile == 0) { tc::mbar_wait(&ctl->act_ready[0], act_phase0); act_phase0 ^= 1; }
+                else              { tc::mbar_wait(&ctl->act_ready[1], act_phase1); act_phase1 ^= 1; }
+            }
+            int hi = op.b_slot;
+            if ((op.flags & F_A_SLOT) && op.a_slot > hi) hi = op.a_slot;
+            const uint32_t need = base + (uint32_t)hi + 1;
+            while (ready < need) {
+                tc::mbar_wait(&ctl->full[ready % kSlots], (ready / kSlots) & 1);
+                ++ready;
+            }
+            tc::tc_fence_after_sync();
+            const uint32_t b_addr = ring_u32 + ((base + (uint32_t)op.b_slot) % kSlots) * kSlotBytes + op.b_off;
+            uint32_t a_addr;
+            uint64_t a_tmpl;
+            if (op.flags & F_A_SLOT) {
+                a_addr = ring_u32 + ((base + (uint32_t)op.a_slot) % kSlots) * kSlotBytes + op.a_off;
+                a_tmpl = kDesc64;
+            } else {
+                a_addr = act_u32 + (uint32_t)op.tile * kActBytes + op.a_off;
+                a_tmpl = kDesc128;
+            }
+            const uint32_t d = tmem + (uint32_t)op.tile * 256u;
+            const uint32_t id = idesc[op.idesc_sel];
+            for (int j = 0; j < op.nk16; ++j)
+                tc::mma_f16_ss(d, a_tmpl | (uint64_t)(((a_addr + 32u * j) >> 4) & 0x3FFF),
+                               kDesc64 | (uint64_t)(((b_addr + 32u * j) >> 4) & 0x3FFF), id,
+                               ((op.flags & F_FIRST) && j == 0) ? 0u : 1u);
+            if (op.rel0 >= 0) tc::mma_commit(&ctl->empty[(base + (uint32_t)op.rel0) % kSlots]);
+            if (op.rel1 >= 0) tc::mma_commit(&ctl->empty[(base + (uint32_t)op.rel1) % kSlots]);
+            if (op.flags & F_COMMIT_ACC) tc::mma_commit(&ctl->acc_full[op.tile]);
+        }
+        base += (uint32_t)n_loads;
+        first_item = false;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* act_all = smem;
+    uint8_t* ring = smem + 2 * kActBytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ring + kSlots * kSlotBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem) & 1023u) != 0) {
+        printf("ddnerf mlp_tc: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    if (warp == 9 && lane == 0) {
+        for (int s = 0; s < kSlots; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 8) tc::tmem_alloc(&ctl->tmem_base, 512);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+
+    if (warp < 8) epilogue_role(g, ctl, act_all, warp, lane);
+    else if (warp == 8) { if (lane == 0) producer_role(g, ctl, ring); }
+    else { if (lane == 0) mma_role(g, ctl, act_all, ring); }
+
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(ctl->tmem_base, 512);
+}
+
+// ---- weight packing: fp32 nn.Linear parameters -> bf16 stage images in program order -----------
+struct PackArgs {
+    ddnerf_mlp_params p;
+    uint8_t* wimg;
+    float* bias;
+    int C;
+};
+
+__device__ __forceinline__ float pack_value(const PackArgs& a, const PackEntry& E, int n, int k) {
+    const int ld = E.p == 0 ? 96 : (E.p == 5 ? 352 : 256);
+    switch (E.kind) {
+        case PK_FWD:
+            return (n < 256 && k < ld) ? __ldg(a.p.w[E.p] + (size_t)n * ld + k) : 0.f;
+        case PK_FWD_DIR:
+            if (n < 128) return k < 283 ? __ldg(a.p.w[10] + (size_t)n * 283 + k) : 0.f;
+            if (n == 128) return k < 256 ? __ldg(a.p.w[9] + k) : 0.f;
+            return 0.f;
+        case PK_FWD_HEADS:
+            if (n < 3) return __ldg(a.p.w[11] + n * 128 + k);
+            if (n < 5 && a.C == 6) return __ldg(a.p.w[12] + (n - 3) * 128 + k);
+            return 0.f;
+        default:
+            return 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
+    const PackEntry E = c_pack_fwd.e[blockIdx.x];
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.wimg + E.dst_off);
+    for (int e = threadIdx.x; e < E.n_total * 32; e += blockDim.x) {
+        const int n = e >> 5, kk = e & 31;
+        dst[tc::sw64_off(n, kk) >> 1] = __float2bfloat16_rn(pack_value(a, E, n, E.k0 + kk));
+    }
+}
+
+// bias table [11][256]: rows 0..8 = layers_xyz.0-7, fc_feat; row 9 = [layers_dir.0 (128) | fc_alpha];
+// row 10 = [fc_rgb (3) | fc_mu_sigma (2)]
+__global__ void __launch_bounds__(256) pack_bias_kernel(const PackArgs a) {
+    const int l = blockIdx.x, c = threadIdx.x;
+    float v = 0.f;
+    if (l <= 8) v = __ldg(a.p.b[l] + c);
+    else if (l == 9) v = c < 128 ? __ldg(a.p.b[10] + c) : (c == 128 ? __ldg(a.p.b[9]) : 0.f);
+    else v = c < 3 ? __ldg(a.p.b[11] + c) : ((c < 5 && a.C == 6) ? __ldg(a.p.b[12] + c - 3) : 0.f);
+    a.bias[l * 256 + c] = v;
+}
+
+// ---- encoder writing bf16 operand images -------------------------------------------------------
+// One thread per (sample row, degree l): the 96 IPE features of a row go to three [128 x 32]
+// SWIZZLE_64B blocks of the item image, the 27 (+5 zero) view-direction features to its dir block.
+__global__ void __launch_bounds__(256) encode_img_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
+                                                         uint8_t* __restrict__ img, int64_t N, int S, int ray_shape,
+                                                         int64_t rows_padded) {
+    const int l = threadIdx.x & 15;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+    if (row >= rows_padded) return;
+    const int64_t item = row / kItemRows;
+    const int T = (int)(row % kItemRows) / 128, r = (int)(row % 128);
+    uint8_t* ib = img + item * kEncItemBytes;
+    float sn[3] = {0.f, 0.f, 0.f}, cs[3] = {0.f, 0.f, 0.f}, d3[3] = {0.f, 0.f, 0.f};
+    const bool valid = row < N * S;
+    if (valid) {
+        const int64_t ray = row / S;
+        const int i = (int)(row - ray * S);
+        const RayGeom g = load_ray(rays, ray);
+        const float* tp = t_vals + ray * (S + 1) + i;
+        const Gauss3 s = cast_interval(g, __ldg(tp), __ldg(tp + 1), ray_shape);
+        ipe_degree(s, l, sn, cs);
+        if (l < 9) dir_group(g, l, d3);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int f = h * 48 + l * 3 + a;
+            const int b = f >> 5, kk = f & 31;
+            const uint32_t blk = b < 2 ? (uint32_t)T * 16384u + (uint32_t)b * 8192u : 32768u + (uint32_t)T * 8192u;
+            *reinterpret_cast<__nv_bfloat16*>(ib + blk + tc::sw64_off(r, kk)) = __float2bfloat16_rn(h ? cs[a] : sn[a]);
+        }
+    }
+    const uint32_t dblk = 49152u + (uint32_t)T * 8192u;
+    if (l < 9) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            *reinterpret_cast<__nv_bfloat16*>(ib + dblk + tc::sw64_off(r, l * 3 + a)) = __float2bfloat16_rn(d3[a]);
+    } else if (l < 14) {
+        *reinterpret_cast<__nv_bfloat16*>(ib + dblk + tc::sw64_off(r, 27 + (l - 9))) = __float2bfloat16_rn(0.f);
+    }
+}
+
+// ---- host: program construction ----------------------------------------------------------------
+struct Builder {
+    Program P{};
+    PackTable K{};
+    int seq = 0;
+    uint32_t woff = 0;
+
+    int load_w(uint32_t bytes, uint16_t kind, uint16_t p, uint16_t n_total, uint16_t k0, int n_chunks = 1) {
+        for (int c = 0; c < n_chunks; ++c)
+            K.e[K.n++] = PackEntry{woff + (uint32_t)c * n_total * 64u, kind, p, n_total, (uint16_t)(k0 + 32 * c)};
+        P.loads[P.n_loads++] = Load{LOAD_W, woff, bytes};
+        woff += bytes;
+        return seq++;
+    }
+    int load_enc(uint32_t off, uint32_t bytes) {
+        P.loads[P.n_loads++] = Load{LOAD_ENC, off, bytes};
+        return seq++;
+    }
+    void mma(int tile, int flags, int nk16, int idesc_sel, int a_slot, uint32_t a_off, int b_slot, uint32_t b_off, int rel0 = -1,
+             int rel1 = -1) {
+        P.mmas[P.n_mmas++] = Mma{(uint8_t)tile, (uint8_t)flags, (uint8_t)nk16, (uint8_t)idesc_sel, (int16_t)a_slot, (int16_t)b_slot,
+                                 a_off, b_off, (int16_t)rel0, (int16_t)rel1};
+    }
+    void epi(int mode, int relu, int save_layer, int ncols, int bias_row, uint32_t save_bytes) {
+        P.epis[P.n_epis++] = Epi{(uint8_t)mode, (uint8_t)relu, (int16_t)save_layer, (uint16_t)ncols, (uint16_t)(bias_row * 256), save_bytes};
+    }
+    // the encoded xyz part (K = 96) of layers 0 and 5: A operand from the item image, 3 weight stages
+    void xyz_part(int p, bool first_layer) {
+        const int x0 = load_enc(0, 16384), x1 = load_enc(16384, 16384), x2 = load_enc(32768, 16384);
+        int w[3];
+        for (int c = 0; c < 3; ++c) w[c] = load_w(16384, PK_FWD, p, 256, 32 * c);
+        for (int T = 0; T < 2; ++T)
+            for (int c = 0; c < 3; ++c) {
+                const int a_slot = c < 2 ? (T == 0 ? x0 : x1) : x2;
+                const uint32_t a_off = c < 2 ? c * 8192u : T * 8192u;
+                int flags = F_A_SLOT;
+                if (first_layer && c == 0) flags |= F_FIRST | F_WAIT_PREV;
+                if (c == 2) flags |= F_COMMIT_ACC;
+                int rel0 = -1, rel1 = -1;
+                if (T == 0) { if (c == 1) rel0 = x0; }
+                else { rel0 = w[c]; if (c == 1) rel1 = x1; if (c == 2) rel1 = x2; }
+                mma(T, flags, 2, 0, a_slot, a_off, w[c], 0, rel0, rel1);
+            }
+    }
+    // a K = 256 accumulation over the act buffer (8 stages), tiles interleaved half a layer apart
+    void h_part(int p, int k0, bool commit) {
+        int w[8];
+        for (int c = 0; c < 8; ++c) w[c] = load_w(16384, PK_FWD, p, 256, k0 + 32 * c);
+        for (int h = 0; h < 2; ++h)
+            for (int T = 0; T < 2; ++T)
+                for (int c = 4 * h; c < 4 * h + 4; ++c) {
+                    int flags = 0;
+                    if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
+                    if (c == 7 && commit) flags |= F_COMMIT_ACC;
+                    mma(T, flags, 2, 0, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
+                }
+    }
+};
+
+// every ring slot an MMA group needs must be loadable: all sequence numbers <= need - kSlots have to
+// be released by earlier groups, else producer and issuer deadlock.
+bool validate(const Program& P, char* why, size_t n) {
+    bool released[kMaxLoads] = {};
+    for (int i = 0; i < P.n_mmas; ++i) {
+        const Mma& op = P.mmas[i];
+        int hi = op.b_slot;
+        if ((op.flags & F_A_SLOT) && op.a_slot > hi) hi = op.a_slot;
+        for (int s = 0; s <= hi - kSlots; ++s)
+            if (!released[s]) { snprintf(why, n, "mma group %d needs slot seq %d but seq %d is still held", i, hi, s); return false; }
+        if (op.rel0 >= 0) released[op.rel0] = true;
+        if (op.rel1 >= 0) released[op.rel1] = true;
+    }
+    for (int s = 0; s < P.n_loads; ++s)
+        if (!released[s]) { snprintf(why, n, "slot seq %d is never released", s); return false; }
+    return true;
+}
+
+struct Programs {
+    Builder fwd;
+    bool ok = false;
+    char why[160] = "";
+};
+
+void build_into(Programs& S) {
+    Builder& b = S.fwd;
+    // layer 0: xyz (96) -> 256
+    b.xyz_part(0, true);
+    b.epi(EPI_ACT, 1, 0, 256, 0, kActBytes);
+    for (int l = 1; l <= 8; ++l) {          // layers_xyz.1-7 and fc_feat (l == 8, no activation)
+        if (l == 5) {                       // cat(xyz, h): weight columns 0..95 = xyz, 96..351 = h
+            b.h_part(5, 96, false);
+            b.xyz_part(5, false);
+        } else {
+            b.h_part(l, 0, true);
+        }
+        b.epi(EPI_ACT, l < 8 ? 1 : 0, l, 256, l, kActBytes);
+    }
+    {   // view branch + density: N = 144 = [layers_dir.0 (128) | fc_alpha | 15 x 0], K = 256 feat + 32 dir
+        int w[9];
+        for (int c = 0; c < 8; ++c) w[c] = b.load_w(144 * 64, PK_FWD_DIR, 10, 144, 32 * c);
+        const int d = b.load_enc(49152, 16384);
+        w[8] = b.load_w(144 * 64, PK_FWD_DIR, 10, 144, 256);
+        for (int h = 0; h < 2; ++h)
+            for (int T = 0; T < 2; ++T) {
+                for (int c = 4 * h; c < 4 * h + 4; ++c)
+                    b.mma(T, c == 0 ? (F_FIRST | F_WAIT_ACT) : 0, 2, 1, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
+                if (h == 1) b.mma(T, F_A_SLOT | F_COMMIT_ACC, 2, 1, d, T * 8192u, w[8], 0, T == 1 ? w[8] : -1, T == 1 ? d : -1);
+            }
+        b.epi(EPI_DIR, 1, 9, 144, 9, 32768);
+    }
+    {   // colour (+ mu, sigma) heads: N = 16, K = 128 (the view-branch activations, k-blocks 0..1)
+        const int wl = b.load_w(4096, PK_FWD_HEADS, 11, 16, 0, 4);
+        for (int T = 0; T < 2; ++T)
+            for (int c = 0; c < 4; ++c) {
+                int flags = 0;
+                if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
+                if (c == 3) flags |= F_COMMIT_ACC;
+                b.mma(T, flags, 2, 2, -1, (c / 2) * 16384u + (c % 2) * 64u, wl, c * 1024u, (T == 1 && c == 3) ? wl : -1);
+            }
+        b.epi(EPI_OUT, 0, -1, 16, 10, 0);
+    }
+    b.K.total_bytes = b.woff;
+    S.ok = validate(b.P, S.why, sizeof(S.why));
+}
+
+Programs* build_programs() {            // host tables are built exactly once
+    static Programs* S = [] { Programs* s = new Programs(); build_into(*s); return s; }();
+    return S;
+}
+
+std::once_flag g_once;
+Programs* g_programs = nullptr;
+int g_upload_rc = 0;
+
+int ensure_programs() {
+    std::call_once(g_once, [] {
+        g_programs = build_programs();
+        if (!g_programs->ok) { g_upload_rc = 1; return; }
+        if (cudaMemcpyToSymbol(c_prog_fwd, &g_programs->fwd.P, sizeof(Program)) != cudaSuccess) g_upload_rc = 2;
+        if (cudaMemcpyToSymbol(c_pack_fwd, &g_programs->fwd.K, sizeof(PackTable)) != cudaSuccess) g_upload_rc = 2;
+        if (cudaFuncSetAttribute(mlp_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+    });
+    return g_upload_rc;
+}
+
+}  // namespace
+}  // namespace ddnerf
+
+using namespace ddnerf;
+
+#define TC_ENSURE(who)                                                                                      \
+    do {                                                                                                    \
+        int rc__ = ensure_programs();                                                                       \
+        DDNERF_CHECK_ARG(rc__ != 1, "%s: invalid kernel program: %s", who, g_programs->why);                \
+        DDNERF_CHECK_ARG(rc__ == 0, "%s: device setup failed (%d): %s", who, rc__, cudaGetErrorString(cudaGetLastError())); \
+    } while (0)
+
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_wimg_bytes(void) {
+    return build_programs()->fwd.woff;
+}
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_bias_floats(void) { return 11 * 256; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_items(int64_t rows) { return (rows + tcmlp::kItemRows - 1) / tcmlp::kItemRows; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_enc_bytes(int64_t rows) { return ddnerf_mlp_tc_items(rows) * tcmlp::kEncItemBytes; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_act_save_bytes(int64_t rows) { return 10 * ddnerf_mlp_tc_items(rows) * 2 * (int64_t)tcmlp::kActBytes; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_mask_save_bytes(int64_t rows) { return 10 * ddnerf_mlp_tc_items(rows) * 2 * 128 * 32; }
+
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_pack(const ddnerf_mlp_params* p, int out_channels, void* wimg, float* bias_pack,
+                                                void* stream) {
+    DDNERF_CHECK_ARG(p && wimg && bias_pack, "mlp_tc_pack: null pointer");
+    DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_pack: out_channels=%d (4 or 6)", out_channels);
+    for (int i = 0; i < (out_channels == 6 ? 13 : 12); ++i) DDNERF_CHECK_ARG(p->w[i] && p->b[i], "mlp_tc_pack: parameter %d is null", i);
+    TC_ENSURE("mlp_tc_pack");
+    PackArgs a{*p, static_cast<uint8_t*>(wimg), bias_pack, out_channels};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    pack_weights_kernel<<<g_programs->fwd.K.n, 256, 0, st>>>(a);
+    pack_bias_kernel<<<11, 256, 0, st>>>(a);
+    DDNERF_LAUNCHED("mlp_tc_pack", 2);
+    return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_encode(const float* rays, const float* t_vals, int64_t N, int S, int ray_shape,
+                                                  void* enc_img, void* stream) {
+    DDNERF_CHECK_ARG(rays && t_vals && enc_img, "mlp_tc_encode: null pointer");
+    DDNERF_CHECK_ARG(ray_shape == 0 || ray_shape == 1, "mlp_tc_encode: ray_shape=%d (0 cone, 1 cylinder)", ray_shape);
+    if (N * S == 0) return 0;
+    const int64_t rows_padded = ddnerf_mlp_tc_items(N * S) * tcmlp::kItemRows;
+    encode_img_kernel<<<ceil_div(rows_padded, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rays, t_vals, static_cast<uint8_t*>(enc_img), N, S, ray_shape, rows_padded);
+    DDNERF_LAUNCHED("mlp_tc_encode", 1);
+    return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float* bias_pack, const void* enc_img, int64_t rows,
+                                                   int out_channels, float* out, void* act_save, void* mask_save, void* stream) {
+    DDNERF_CHECK_ARG(wimg && bias_pack && enc_img && out, "mlp_tc_forward: null pointer");
+    DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_forward: out_channels=%d (4 or 6)", out_channels);
+    DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_forward: the bf16 MLP needs an sm_100 device (tcgen05)");
+    if (rows == 0) return 0;
+    TC_ENSURE("mlp_tc_forward");
+    const int64_t n_items = ddnerf_mlp_tc_items(rows);
+    DDNERF_CHECK_ARG(n_items < (1 << 30), "mlp_tc_forward: too many rows");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ChainArgs g{static_cast<const uint8_t*>(wimg), bias_pack, static_cast<const uint8_t*>(enc_img), out,
+                static_cast<uint8_t*>(act_save), static_cast<uint32_t*>(mask_save), rows, (int)n_items, out_channels};
+    const int grid = (int)std::min<int64_t>(n_items, sms);
+    mlp_tc_chain_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    DDNERF_LAUNCHED("mlp_tc_forward", 1);
+    return 0;
+}

@@ -98,6 +98,28 @@ int ddnerf_mlp_f32_backward(const ddnerf_mlp_params* p, const ddnerf_mlp_grads* 
                             const float* grad_out, int64_t rows, int out_channels, float* dx,
                             void* workspace, void* stream);
 
+/* ---- K1, bf16 throughput mode: fused tcgen05 chain (csrc/mlp_tc.cu) ----------------------------
+ * Weights are re-packed (after every optimizer step) into bf16 stage images in the order the
+ * kernel streams them; biases into an fp32 table.  Rows are processed in 256-row work items; the
+ * encoder writes the bf16 operand image of every item (IPE xyz blocks + view-direction block). */
+int64_t ddnerf_mlp_tc_wimg_bytes(void);
+int64_t ddnerf_mlp_tc_bias_floats(void);
+int64_t ddnerf_mlp_tc_items(int64_t rows);
+int64_t ddnerf_mlp_tc_enc_bytes(int64_t rows);
+int64_t ddnerf_mlp_tc_act_save_bytes(int64_t rows);
+int64_t ddnerf_mlp_tc_mask_save_bytes(int64_t rows);
+int ddnerf_mlp_tc_pack(const ddnerf_mlp_params* p, int out_channels, void* wimg, float* bias_pack,
+                       void* stream);
+/* cast_rays + integrated_pos_enc + positional_encoding (models/models.py:117-133) -> bf16 images */
+int ddnerf_mlp_tc_encode(const float* rays, const float* t_vals, int64_t N, int S, int ray_shape,
+                         void* enc_img, void* stream);
+/* MipNeRFModel / DepthMipNeRFModel forward (base_architectures.py:40-61 / 103-126) over `rows`
+ * samples; out [rows, C] fp32.  act_save / mask_save: NULL for inference, else the areas sized by
+ * the two *_save_bytes functions (kept for the backward kernels). */
+int ddnerf_mlp_tc_forward(const void* wimg, const float* bias_pack, const void* enc_img,
+                          int64_t rows, int out_channels, float* out, void* act_save,
+                          void* mask_save, void* stream);
+
 /* Descriptor self-test of the tcgen05 path (test infrastructure of the bf16 MLP): one CTA computes
  * D[128,N] = A.B^T from two operand tile images given in their shared-memory byte layout, with the
  * shared-memory descriptors (start address 0), instruction descriptor and per-k16-step address

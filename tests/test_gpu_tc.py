@@ -101,3 +101,66 @@ def test_mnmajor_sw128_both(N, K):
     d = _run(a_img, b_img, N, K // 16, a_desc, b_desc, tcimg.idesc_bf16(128, N, 1, 1),
              (2048, 1 << 20, 0, 2048, 1 << 20, 0))
     _check(d, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused bf16 MLP forward (csrc/mlp_tc.cu)
+# ---------------------------------------------------------------------------------------------
+def _bf(x):
+    return x.bfloat16().float()
+
+
+def mlp_forward_bf16_emulated(params, x):
+    """The kernel's arithmetic restated in torch: bf16 weights and activations, fp32 accumulation and
+    bias, density from the bf16 fc_feat output, heads from the bf16 view-branch activations."""
+    import torch.nn.functional as F
+    W = {k: _bf(v) if k.endswith("weight") else v for k, v in params.items()}
+    xyz, dirs = _bf(x[..., :96]), _bf(x[..., 96:])
+    h = _bf(F.relu(F.linear(xyz, W["layers_xyz.0.weight"], W["layers_xyz.0.bias"])))
+    for i in range(1, 8):
+        inp = torch.cat((xyz, h), -1) if i == 5 else h
+        h = _bf(F.relu(F.linear(inp, W[f"layers_xyz.{i}.weight"], W[f"layers_xyz.{i}.bias"])))
+    feat = _bf(F.linear(h, W["fc_feat.weight"], W["fc_feat.bias"]))
+    alpha = F.linear(feat, W["fc_alpha.weight"], W["fc_alpha.bias"])
+    hd = _bf(F.relu(F.linear(torch.cat((feat, dirs), -1), W["layers_dir.0.weight"], W["layers_dir.0.bias"])))
+    out = [F.linear(hd, W["fc_rgb.weight"], W["fc_rgb.bias"]), alpha]
+    if "fc_mu_sigma.weight" in W:
+        out.append(F.linear(hd, W["fc_mu_sigma.weight"], W["fc_mu_sigma.bias"]))
+    return torch.cat(out, -1)
+
+
+def _tc_forward(depth_head, N, S, kind, seed):
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200 import mlp_tc
+    from ddnerf_b200.models import base_architectures as BA
+    from ddnerf_b200.rays import synth_rays
+    params = orc.init_mlp_params(depth_head, seed=seed)
+    ro, rd, rad, near, far = synth_rays(kind, N, seed=seed)
+    rays = orc.pack_rays(ro, rd, rad, near, far)
+    g = torch.Generator().manual_seed(seed)
+    t_vals = orc.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], S, t_rand=torch.rand(N, S + 1, generator=g))
+    x = orc.encode_rows(rays, t_vals)
+    ref32 = orc.mlp_forward(params, x)
+    ref16 = mlp_forward_bf16_emulated(params, x)
+    net = (BA.DepthMipNeRFModel if depth_head else BA.MipNeRFModel)(
+        hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True)
+    net.load_state_dict(params)
+    net.to("cuda")
+    with torch.no_grad():
+        out = mlp_tc.forward_only(net, rays.cuda(), t_vals.cuda())
+    torch.cuda.synchronize()
+    return out.cpu(), ref16, ref32
+
+
+@pytest.mark.parametrize("depth_head,N,S,kind", [(False, 8, 32, "blender"), (True, 37, 16, "blender"),
+                                                 (True, 300, 32, "ff"), (False, 2048, 64, "360")])
+def test_mlp_tc_forward(depth_head, N, S, kind):
+    """Raw network outputs: tight against the bf16-emulating restatement (same rounding points;
+    residual = accumulation order + rare 1-ulp bf16 flips), loose against the fp32 oracle."""
+    out, ref16, ref32 = _tc_forward(depth_head, N, S, kind, seed=5)
+    assert torch.isfinite(out).all()
+    err16 = (out - ref16).abs().max().item()
+    err32 = (out - ref32).abs().max().item()
+    print(f"bf16 MLP forward: max|out-emulated| {err16:.3e}  max|out-fp32| {err32:.3e}  (|ref| max {ref32.abs().max():.3f})")
+    assert err16 < 2e-3
+    assert err32 < 5e-3
