@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mlp-mode", default=os.environ.get("DDNERF_MLP_MODE", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--mlp-mode", default=os.environ.get("DDNERF_MLP_MODE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ddnerf_mlp_tc_pack": (c_i, [ctypes.POINTER(MlpPtrs), c_i, c_p, c_p, c_p]),
     "ddnerf_mlp_tc_encode": (c_i, [c_p, c_p, c_l, c_i, c_i, c_p, c_p]),
     "ddnerf_mlp_tc_forward": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
+    "ddnerf_mlp_tc_backward_dx": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p]),
+    "ddnerf_mlp_tc_backward_dw": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(MlpPtrs), c_l, c_i, c_p]),
     "ddnerf_tc_gemm_selftest": (c_i, [c_p, c_l, c_p, c_l, c_p, c_i, c_i, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                       ctypes.POINTER(ctypes.c_uint32), c_p]),
     "ddnerf_composite_forward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 7 + [c_l, c_i, c_p]),

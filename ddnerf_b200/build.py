@@ -27,6 +27,7 @@ SOURCES = {
     "dploss.cu": ["-fmad=false"],
     "mlp_f32.cu": [],
     "mlp_tc.cu": [],
+    "mlp_tc_dw.cu": [],
     "tc_selftest.cu": [],
     "train_tail.cu": [],
 }

@@ -1,23 +1,31 @@
-// K1 (bf16 throughput mode): the NeRF MLP of models/base_architectures.py:3-126 as ONE persistent,
-// warp-specialised tcgen05 kernel per pass.  A CTA owns a 256-row work item (two 128-row tiles);
-// all 11 GEMMs of the network run back to back with the activations resident on chip:
+// K1 (bf16 throughput mode): the NeRF MLP of models/base_architectures.py:3-126 as persistent,
+// warp-specialised tcgen05 chain kernels.  A CTA owns a 256-row work item (two 128-row tiles); all
+// GEMMs of the network run back to back with the activations resident on chip:
 //
 //   producer warp  : walks the static load program, streaming 16 KB weight stages (and the encoded
 //                    xyz / view-direction blocks) from L2 into a 6-slot shared-memory ring with
 //                    bulk async copies (TMA engine) completing on mbarriers;
-//   MMA warp       : one thread issues tcgen05.mma (M=128, N=256/144/16, K=16, bf16 -> fp32 in
-//                    TMEM); the two tiles share every weight stage and are interleaved half a layer
-//                    apart so that one tile's epilogue overlaps the other tile's MMAs;
+//   MMA warp       : issues tcgen05.mma (M=128, N=256/144/16, K=16, bf16 -> fp32 in TMEM) from a
+//                    host-resolved op table; the two tiles share every weight stage and are
+//                    interleaved half a layer apart so that one tile's epilogue overlaps the other
+//                    tile's MMAs;
 //   8 epilogue warps: tcgen05.ld the accumulator, add bias, ReLU, convert to bf16 and write the next
 //                    layer's A operand in place (K-major SWIZZLE_128B); density / colour / (mu, sigma)
 //                    heads are extra columns of the last two GEMMs and leave as fp32.
 //
+// FORWARD (program 0): layers_xyz.0-7, fc_feat, [layers_dir.0 | fc_alpha], [fc_rgb | fc_mu_sigma].
 // The skip connection cat(xyz, h) of layer 5 and the cat(feat, dirs) of the view branch are extra
 // K-chunks of the same accumulation whose A operand is the encoded block in the ring.  In training
 // the epilogues also store every layer's bf16 activations (tile images, bulk stores) and ReLU sign
-// bitmasks for the backward kernels.
+// bitmasks.
+//
+// BACKWARD (program 1, the dX chain): dZ_dir = (g_rgb.W_rgb + g_musig.W_musig) * relu' on CUDA cores,
+// then dZ_feat = [dZ_dir | g_density] . [W_dir[:, :256] ; w_alpha], dZ_l = (dZ_{l+1} . W_{l+1}) *
+// relu'_l down to layer 0, with transposed weight stages.  Every dZ tile image is stored for the
+// weight-gradient kernel (mlp_tc_dw.cu).
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 #define DDNERF_TC_WATCHDOG 1
 
@@ -29,16 +37,17 @@ namespace {
 
 using namespace tcmlp;
 
-__constant__ Program c_prog_fwd;
-__constant__ PackTable c_pack_fwd;
+__constant__ Program c_prog[2];          // 0 forward, 1 backward (dX chain)
+__constant__ PackTable c_pack;
 
 struct ChainArgs {
-    const uint8_t* wimg;      // packed weight stages (program order)
-    const float* bias;        // packed fp32 biases, [n_epis][256]
-    const uint8_t* enc;       // encoded-feature images, [n_items][64 KB]
-    float* out;               // [rows, C]
-    uint8_t* act_save;        // [layers][n_tiles][64 KB] or null
-    uint32_t* mask_save;      // [layers][n_tiles][128][8] or null
+    const uint8_t* wimg;      // packed weight stages of this program (program order)
+    const float* bias;        // fwd: packed fp32 biases, [n_epis][256]
+    const uint8_t* enc;       // fwd: encoded-feature images, [n_items][64 KB]
+    float* out;               // fwd: [rows, C]
+    const float* gout;        // bwd: [rows, C] cotangent of the output
+    uint8_t* save;            // fwd: act_save or null; bwd: dz_save.  [layers][n_tiles][64 KB]
+    uint32_t* mask;           // [layers][n_tiles][128][8]: fwd writes (or null), bwd reads
     int64_t rows;
     int n_items, C;
 };
@@ -54,8 +63,16 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 32 bf16 (16 packed words) of row `row`, columns [c0, c0+32), into the K-major SWIZZLE_128B act buffer
+__device__ __forceinline__ void store_chunk32(uint32_t act_u32, int row, int c0, const uint32_t (&pk)[16]) {
+    const uint32_t base = act_u32 + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)row * 128u;
+    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_shared_v4(base + ((((ch0 + i) ^ (uint32_t)row) & 7u) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
 
-// ---- epilogue pieces ------------------------------------------------------------------------
+// ---- forward epilogue -----------------------------------------------------------------------
 // 32 accumulator columns [c0, c0+32) of this thread's row: + bias, optional ReLU, -> bf16, stored as
 // four 16-byte chunks of the act buffer.  Returns the sign bitmask (bit i = value i > 0).
 __device__ __forceinline__ uint32_t epi_chunk32(uint32_t tmem_addr, const float* __restrict__ bias_s, int c0, bool relu,
@@ -78,27 +95,24 @@ __device__ __forceinline__ uint32_t epi_chunk32(uint32_t tmem_addr, const float*
         pk[i / 2] = tc::pack_bf16(x0, x1);
         pk[i / 2 + 1] = tc::pack_bf16(x2, x3);
     }
-    const uint32_t base = act_u32 + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)row * 128u;
-    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        st_shared_v4(base + ((((ch0 + i) ^ (uint32_t)row) & 7u) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    store_chunk32(act_u32, row, c0, pk);
     return m;
 }
 
-__device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+__device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+    const Program& P = c_prog[0];
     const int T = warp >> 2, q = warp & 3, row = q * 32 + lane;
     const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
     const uint32_t tmem_row = ctl->tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
     float* bias_s = ctl->bias[T];
     const int bar_id = 1 + T;
     const int n_tiles = g.n_items * 2;
-    const int n_epis = c_prog_fwd.n_epis;
+    const int n_epis = P.n_epis;
     uint32_t acc_phase = 0;
     bool store_pending = false;
 
     {   // bias of the first epilogue
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(g.bias + c_prog_fwd.epis[0].bias_off) + row);
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(g.bias + P.epis[0].bias_off) + row);
         bias_s[2 * row] = b0.x;
         bias_s[2 * row + 1] = b0.y;
         named_bar(bar_id, 128);
@@ -107,13 +121,13 @@ __device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all
         const int tile_g = item * 2 + T;
         const int64_t row_g = (int64_t)tile_g * 128 + row;
         for (int e = 0; e < n_epis; ++e) {
-            const Epi E = c_prog_fwd.epis[e];
+            const Epi E = P.epis[e];
             const int en = (e + 1 == n_epis) ? 0 : e + 1;
-            const float2 nb = __ldg(reinterpret_cast<const float2*>(g.bias + c_prog_fwd.epis[en].bias_off) + row);
+            const float2 nb = __ldg(reinterpret_cast<const float2*>(g.bias + P.epis[en].bias_off) + row);
             tc::mbar_wait(&ctl->acc_full[T], acc_phase);
             acc_phase ^= 1;
             tc::tc_fence_after_sync();
-            if (g.act_save) {            // the previous bulk store of this act buffer must have read it
+            if (g.save) {                // the previous bulk store of this act buffer must have read it
                 if (row == 0 && store_pending) { tc::bulk_wait_read<0>(); store_pending = false; }
                 named_bar(bar_id, 128);
             }
@@ -131,8 +145,8 @@ __device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all
                     tc::tmem_ld_wait();
                     if (row_g < g.rows) g.out[row_g * g.C + 3] = __uint_as_float(v[0]) + bias_s[128];
                 }
-                if (g.mask_save && E.save_layer >= 0 && E.relu) {
-                    uint4* mp = reinterpret_cast<uint4*>(g.mask_save + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8);
+                if (g.mask && E.save_layer >= 0 && E.relu) {
+                    uint4* mp = reinterpret_cast<uint4*>(g.mask + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8);
                     mp[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
                     mp[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
                 }
@@ -156,8 +170,8 @@ __device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all
             named_bar(bar_id, 128);
             if (row == 0) {
                 tc::mbar_arrive(&ctl->act_ready[T]);
-                if (g.act_save && E.save_layer >= 0) {
-                    tc::bulk_s2g(g.act_save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
+                if (g.save && E.save_layer >= 0) {
+                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
                                  E.save_bytes);
                     tc::bulk_commit();
                     store_pending = true;
@@ -171,75 +185,176 @@ __device__ void epilogue_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all
     if (row == 0) tc::bulk_wait_all<0>();
 }
 
+// ---- backward epilogue ------------------------------------------------------------------------
+__device__ __forceinline__ float masked(float x, uint32_t m, int bit) { return ((m >> bit) & 1u) ? x : 0.f; }
+
+__device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+    const Program& P = c_prog[1];
+    const int T = warp >> 2, q = warp & 3, row = q * 32 + lane;
+    const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
+    const uint32_t tmem_row = ctl->tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
+    const int bar_id = 1 + T;
+    const int n_tiles = g.n_items * 2;
+    const int n_epis = P.n_epis;
+    uint32_t acc_phase = 0;
+    bool store_pending = false;
+
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int tile_g = item * 2 + T;
+        const int64_t row_g = (int64_t)tile_g * 128 + row;
+        for (int e = 0; e < n_epis; ++e) {
+            const Epi E = P.epis[e];
+            uint32_t mk[8];
+            if (E.mask_layer >= 0) {
+                const uint4* mp = reinterpret_cast<const uint4*>(g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8);
+                const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
+                mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) mk[c] = 0xffffffffu;
+            }
+            if (E.mode != EPI_BWD_IN) {
+                tc::mbar_wait(&ctl->acc_full[T], acc_phase);
+                acc_phase ^= 1;
+                tc::tc_fence_after_sync();
+            }
+            if (row == 0 && store_pending) { tc::bulk_wait_read<0>(); store_pending = false; }
+            named_bar(bar_id, 128);
+            if (E.mode == EPI_BWD_IN) {
+                // dZ_dir = (g_rgb . W_rgb + g_musig . W_musig) * relu'(dir layer); column 128 = g_density
+                const float* w_rgb = g.bias + kHeadWRow * 256;          // aligned fp32 copies of the head weights
+                const float* w_musig = w_rgb + 3 * 256;
+                float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (row_g < g.rows) {
+                    const float* gp = g.gout + row_g * g.C;
+                    for (int c = 0; c < g.C; ++c) gr[c] = __ldg(gp + c);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int col = c * 32 + i;
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb + col));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb + 256 + col));
+                        const float4 w2 = __ldg(reinterpret_cast<const float4*>(w_rgb + 512 + col));
+                        float x0 = gr[0] * w0.x + gr[1] * w1.x + gr[2] * w2.x;
+                        float x1 = gr[0] * w0.y + gr[1] * w1.y + gr[2] * w2.y;
+                        float x2 = gr[0] * w0.z + gr[1] * w1.z + gr[2] * w2.z;
+                        float x3 = gr[0] * w0.w + gr[1] * w1.w + gr[2] * w2.w;
+                        if (g.C == 6) {
+                            const float4 u0 = __ldg(reinterpret_cast<const float4*>(w_musig + col));
+                            const float4 u1 = __ldg(reinterpret_cast<const float4*>(w_musig + 256 + col));
+                            x0 += gr[4] * u0.x + gr[5] * u1.x;
+                            x1 += gr[4] * u0.y + gr[5] * u1.y;
+                            x2 += gr[4] * u0.z + gr[5] * u1.z;
+                            x3 += gr[4] * u0.w + gr[5] * u1.w;
+                        }
+                        pk[i / 2] = tc::pack_bf16(masked(x0, mk[c], i), masked(x1, mk[c], i + 1));
+                        pk[i / 2 + 1] = tc::pack_bf16(masked(x2, mk[c], i + 2), masked(x3, mk[c], i + 3));
+                    }
+                    store_chunk32(act_u32, row, c * 32, pk);
+                }
+                const uint32_t b2 = act_u32 + 2u * 16384u + (uint32_t)row * 128u;
+                // columns 128..135 = [g_density, g_r, g_g, g_b, g_mu, g_sigma, 0, 0]: column 128 is the K extension of
+                // the next GEMM (weight rows 129..143 are zero); all six feed the head gradients in mlp_tc_dw.cu
+                st_shared_v4(b2 + (((0u ^ (uint32_t)row) & 7u) << 4), tc::pack_bf16(gr[3], gr[0]), tc::pack_bf16(gr[1], gr[2]),
+                             tc::pack_bf16(gr[4], gr[5]), 0u);
+                st_shared_v4(b2 + (((1u ^ (uint32_t)row) & 7u) << 4), 0u, 0u, 0u, 0u);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_row + c * 32, v);
+                    tc::tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2)
+                        pk[i / 2] = tc::pack_bf16(masked(__uint_as_float(v[i]), mk[c], i), masked(__uint_as_float(v[i + 1]), mk[c], i + 1));
+                    store_chunk32(act_u32, row, c * 32, pk);
+                }
+            }
+            tc::tc_fence_before_sync();
+            tc::fence_proxy_async_smem();
+            named_bar(bar_id, 128);
+            if (row == 0) {
+                if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
+                tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes, E.save_bytes);
+                tc::bulk_commit();
+                store_pending = true;
+            }
+        }
+    }
+    if (row == 0) tc::bulk_wait_all<0>();
+}
+
+template <int PI>
 __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
-    uint32_t seq = 0;
-    const int n_loads = c_prog_fwd.n_loads;
+    const Program& P = c_prog[PI];
+    const int n_loads = P.n_loads;                         // multiple of kSlots
+    uint32_t phase = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const uint8_t* enc = g.enc + (size_t)item * kEncItemBytes;
-        for (int i = 0; i < n_loads; ++i, ++seq) {
-            const Load L = c_prog_fwd.loads[i];
-            const uint32_t slot = seq % kSlots, phase = (seq / kSlots) & 1;
+        int slot = 0;
+        for (int i = 0; i < n_loads; ++i) {
+            const Load L = P.loads[i];
             tc::mbar_wait(&ctl->empty[slot], phase ^ 1);
             const uint8_t* src = (L.kind == LOAD_W ? g.wimg : enc) + L.off;
             tc::mbar_expect_tx(&ctl->full[slot], L.bytes);
             tc::bulk_g2s(ring + slot * kSlotBytes, src, L.bytes, &ctl->full[slot]);
+            if (++slot == kSlots) { slot = 0; phase ^= 1; }
         }
     }
 }
 
-__device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, uint8_t* ring) {
-    const uint32_t act_u32 = tc::smem_u32(act_all), ring_u32 = tc::smem_u32(ring);
-    constexpr uint64_t kDesc128 = tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128);
-    constexpr uint64_t kDesc64 = tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64);
-    const uint32_t idesc[3] = {tc::idesc_bf16(128, 256, 0, 0), tc::idesc_bf16(128, 144, 0, 0), tc::idesc_bf16(128, 16, 0, 0)};
+// The whole warp walks the op table (uniform control flow); one elected lane issues the MMAs and commits.
+template <int PI>
+__device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
+    const Program& P = c_prog[PI];
+    const uint32_t base16 = smem_base >> 4;
     const uint32_t tmem = ctl->tmem_base;
-    const int n_mmas = c_prog_fwd.n_mmas, n_loads = c_prog_fwd.n_loads;
-    uint32_t base = 0, ready = 0, act_phase0 = 0, act_phase1 = 0;
+    const uint32_t full0 = tc::smem_u32(&ctl->full[0]), empty0 = tc::smem_u32(&ctl->empty[0]);
+    const uint32_t acc0 = tc::smem_u32(&ctl->acc_full[0]), act0 = tc::smem_u32(&ctl->act_ready[0]);
+    const int n_mmas = P.n_mmas;
+    uint32_t ready_slot = 0, ready_phase = 0, act_phase = 0;
     bool first_item = true;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         for (int i = 0; i < n_mmas; ++i) {
-            const Mma op = c_prog_fwd.mmas[i];
-            if ((op.flags & F_WAIT_ACT) || ((op.flags & F_WAIT_PREV) && !first_item)) {
-                if (op.tile == 0) { tc::mbar_wait(&ctl->act_ready[0], act_phase0); act_phase0 ^= 1; }
-                else              { tc::mbar_wait(&ctl->act_ready[1], act_phase1); act_phase1 ^= 1; }
+            const uint4 q0 = *reinterpret_cast<const uint4*>(&P.mmas[i]);
+            const uint4 q1 = *(reinterpret_cast<const uint4*>(&P.mmas[i]) + 1);
+            const uint32_t nk16 = (q1.y >> 16) & 0xFFu, flags = q1.y >> 24;
+            const uint32_t tile = q1.z & 0xFFu, n_wait = (q1.z >> 8) & 0xFFu, rel0 = (q1.z >> 16) & 0xFFu, rel1 = q1.z >> 24;
+            if ((flags & F_WAIT_ACT) || ((flags & F_WAIT_PREV) && !first_item)) {
+                tc::mbar_wait_u32(act0 + tile * 8u, (act_phase >> tile) & 1u);
+                act_phase ^= 1u << tile;
             }
-            int hi = op.b_slot;
-            if ((op.flags & F_A_SLOT) && op.a_slot > hi) hi = op.a_slot;
-            const uint32_t need = base + (uint32_t)hi + 1;
-            while (ready < need) {
-                tc::mbar_wait(&ctl->full[ready % kSlots], (ready / kSlots) & 1);
-                ++ready;
+            for (uint32_t w = 0; w < n_wait; ++w) {
+                tc::mbar_wait_u32(full0 + ready_slot * 8u, ready_phase);
+                if (++ready_slot == kSlots) { ready_slot = 0; ready_phase ^= 1u; }
             }
             tc::tc_fence_after_sync();
-            const uint32_t b_addr = ring_u32 + ((base + (uint32_t)op.b_slot) % kSlots) * kSlotBytes + op.b_off;
-            uint32_t a_addr;
-            uint64_t a_tmpl;
-            if (op.flags & F_A_SLOT) {
-                a_addr = ring_u32 + ((base + (uint32_t)op.a_slot) % kSlots) * kSlotBytes + op.a_off;
-                a_tmpl = kDesc64;
-            } else {
-                a_addr = act_u32 + (uint32_t)op.tile * kActBytes + op.a_off;
-                a_tmpl = kDesc128;
+            if (tc::elect_one()) {
+                const uint64_t a = ((uint64_t)q0.z << 32) | (uint64_t)(base16 + q0.x);
+                const uint64_t b = ((uint64_t)q0.w << 32) | (uint64_t)(base16 + q0.y);
+                const uint32_t d = tmem + (q1.y & 0xFFFFu);
+                if (nk16 > 0) tc::mma_f16_ss(d, a, b, q1.x, (flags & F_FIRST) ? 0u : 1u);
+                if (nk16 > 1) tc::mma_f16_ss(d, a + 2, b + 2, q1.x, 1u);
+                if (rel0 != 0xFFu) tc::mma_commit_u32(empty0 + rel0 * 8u);
+                if (rel1 != 0xFFu) tc::mma_commit_u32(empty0 + rel1 * 8u);
+                if (flags & F_COMMIT_ACC) tc::mma_commit_u32(acc0 + tile * 8u);
             }
-            const uint32_t d = tmem + (uint32_t)op.tile * 256u;
-            const uint32_t id = idesc[op.idesc_sel];
-            for (int j = 0; j < op.nk16; ++j)
-                tc::mma_f16_ss(d, a_tmpl | (uint64_t)(((a_addr + 32u * j) >> 4) & 0x3FFF),
-                               kDesc64 | (uint64_t)(((b_addr + 32u * j) >> 4) & 0x3FFF), id,
-                               ((op.flags & F_FIRST) && j == 0) ? 0u : 1u);
-            if (op.rel0 >= 0) tc::mma_commit(&ctl->empty[(base + (uint32_t)op.rel0) % kSlots]);
-            if (op.rel1 >= 0) tc::mma_commit(&ctl->empty[(base + (uint32_t)op.rel1) % kSlots]);
-            if (op.flags & F_COMMIT_ACC) tc::mma_commit(&ctl->acc_full[op.tile]);
+            __syncwarp();
         }
-        base += (uint32_t)n_loads;
         first_item = false;
     }
 }
 
+template <int PI>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* act_all = smem;
-    uint8_t* ring = smem + 2 * kActBytes;
+    uint8_t* ring = smem + kRingOff;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ring + kSlots * kSlotBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0 && (tc::smem_u32(smem) & 1023u) != 0) {
@@ -256,9 +371,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainAr
     __syncthreads();
     tc::tc_fence_after_sync();
 
-    if (warp < 8) epilogue_role(g, ctl, act_all, warp, lane);
-    else if (warp == 8) { if (lane == 0) producer_role(g, ctl, ring); }
-    else { if (lane == 0) mma_role(g, ctl, act_all, ring); }
+    if (warp < 8) {
+        if (PI == 0) epilogue_fwd(g, ctl, act_all, warp, lane);
+        else epilogue_bwd(g, ctl, act_all, warp, lane);
+    } else if (warp == 8) {
+        if (lane == 0) producer_role<PI>(g, ctl, ring);
+    } else {
+        mma_role<PI>(g, ctl, tc::smem_u32(smem));
+    }
 
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -273,10 +393,11 @@ struct PackArgs {
     int C;
 };
 
+// element (n, k) of the stage's B operand  (D[m, n] += A[m, k] . B[n, k])
 __device__ __forceinline__ float pack_value(const PackArgs& a, const PackEntry& E, int n, int k) {
     const int ld = E.p == 0 ? 96 : (E.p == 5 ? 352 : 256);
     switch (E.kind) {
-        case PK_FWD:
+        case PK_FWD:                       // B[n][k] = W_p[n][k]
             return (n < 256 && k < ld) ? __ldg(a.p.w[E.p] + (size_t)n * ld + k) : 0.f;
         case PK_FWD_DIR:
             if (n < 128) return k < 283 ? __ldg(a.p.w[10] + (size_t)n * 283 + k) : 0.f;
@@ -286,13 +407,19 @@ __device__ __forceinline__ float pack_value(const PackArgs& a, const PackEntry& 
             if (n < 3) return __ldg(a.p.w[11] + n * 128 + k);
             if (n < 5 && a.C == 6) return __ldg(a.p.w[12] + (n - 3) * 128 + k);
             return 0.f;
+        case PK_BWD:                       // B[n][k] = W_p[k][n0 + n]  (dX = dZ . W)
+            return k < 256 ? __ldg(a.p.w[E.p] + (size_t)k * ld + E.n0 + n) : 0.f;
+        case PK_BWD_DIR:                   // k < 128: W_dir[k][n]; k == 128: w_alpha[n]  (n = feat index)
+            if (k < 128) return __ldg(a.p.w[10] + (size_t)k * 283 + n);
+            if (k == 128) return __ldg(a.p.w[9] + n);
+            return 0.f;
         default:
             return 0.f;
     }
 }
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
-    const PackEntry E = c_pack_fwd.e[blockIdx.x];
+    const PackEntry E = c_pack.e[blockIdx.x];
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.wimg + E.dst_off);
     for (int e = threadIdx.x; e < E.n_total * 32; e += blockDim.x) {
         const int n = e >> 5, kk = e & 31;
@@ -300,14 +427,17 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
     }
 }
 
-// bias table [11][256]: rows 0..8 = layers_xyz.0-7, fc_feat; row 9 = [layers_dir.0 (128) | fc_alpha];
-// row 10 = [fc_rgb (3) | fc_mu_sigma (2)]
+// bias table [16][256]: rows 0..8 = layers_xyz.0-7, fc_feat; row 9 = [layers_dir.0 (128) | fc_alpha];
+// row 10 = [fc_rgb (3) | fc_mu_sigma (2)]; rows 11..13 = fc_rgb.weight rows, 14..15 = fc_mu_sigma.weight
+// rows (fp32 copies at aligned addresses, read by the backward chain's first epilogue)
 __global__ void __launch_bounds__(256) pack_bias_kernel(const PackArgs a) {
     const int l = blockIdx.x, c = threadIdx.x;
     float v = 0.f;
     if (l <= 8) v = __ldg(a.p.b[l] + c);
     else if (l == 9) v = c < 128 ? __ldg(a.p.b[10] + c) : (c == 128 ? __ldg(a.p.b[9]) : 0.f);
-    else v = c < 3 ? __ldg(a.p.b[11] + c) : ((c < 5 && a.C == 6) ? __ldg(a.p.b[12] + c - 3) : 0.f);
+    else if (l == 10) v = c < 3 ? __ldg(a.p.b[11] + c) : ((c < 5 && a.C == 6) ? __ldg(a.p.b[12] + c - 3) : 0.f);
+    else if (l <= 13) v = c < 128 ? __ldg(a.p.w[11] + (l - 11) * 128 + c) : 0.f;
+    else v = (c < 128 && a.C == 6) ? __ldg(a.p.w[12] + (l - 14) * 128 + c) : 0.f;
     a.bias[l * 256 + c] = v;
 }
 
@@ -355,15 +485,28 @@ __global__ void __launch_bounds__(256) encode_img_kernel(const float* __restrict
 }
 
 // ---- host: program construction ----------------------------------------------------------------
+constexpr uint32_t kHi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
+constexpr uint32_t kHi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) >> 32);
+
+struct RawMma {
+    int tile, flags, nk16, n;            // n: MMA N (instruction descriptor)
+    int a_seq;                           // ring stage holding A, -1: the tile's act buffer
+    uint32_t a_off;
+    int b_seq;                           // ring stage holding B (-1: none, nk16 == 0)
+    uint32_t b_off;
+    int rel0, rel1;                      // ring stages released after this group
+};
+
 struct Builder {
     Program P{};
-    PackTable K{};
+    PackTable* K = nullptr;
+    std::vector<RawMma> ops;
     int seq = 0;
-    uint32_t woff = 0;
+    uint32_t woff = 0, wbase = 0;        // wbase: byte offset of this program's region in the weight image
 
-    int load_w(uint32_t bytes, uint16_t kind, uint16_t p, uint16_t n_total, uint16_t k0, int n_chunks = 1) {
+    int load_w(uint32_t bytes, uint16_t kind, uint16_t p, uint16_t n_total, uint16_t k0, uint16_t n0 = 0, int n_chunks = 1) {
         for (int c = 0; c < n_chunks; ++c)
-            K.e[K.n++] = PackEntry{woff + (uint32_t)c * n_total * 64u, kind, p, n_total, (uint16_t)(k0 + 32 * c)};
+            K->e[K->n++] = PackEntry{wbase + woff + (uint32_t)c * n_total * 64u, kind, p, n_total, (uint16_t)(k0 + 32 * c), n0, 0};
         P.loads[P.n_loads++] = Load{LOAD_W, woff, bytes};
         woff += bytes;
         return seq++;
@@ -372,13 +515,13 @@ struct Builder {
         P.loads[P.n_loads++] = Load{LOAD_ENC, off, bytes};
         return seq++;
     }
-    void mma(int tile, int flags, int nk16, int idesc_sel, int a_slot, uint32_t a_off, int b_slot, uint32_t b_off, int rel0 = -1,
+    void mma(int tile, int flags, int nk16, int n, int a_seq, uint32_t a_off, int b_seq, uint32_t b_off, int rel0 = -1,
              int rel1 = -1) {
-        P.mmas[P.n_mmas++] = Mma{(uint8_t)tile, (uint8_t)flags, (uint8_t)nk16, (uint8_t)idesc_sel, (int16_t)a_slot, (int16_t)b_slot,
-                                 a_off, b_off, (int16_t)rel0, (int16_t)rel1};
+        ops.push_back(RawMma{tile, flags, nk16, n, a_seq, a_off, b_seq, b_off, rel0, rel1});
     }
-    void epi(int mode, int relu, int save_layer, int ncols, int bias_row, uint32_t save_bytes) {
-        P.epis[P.n_epis++] = Epi{(uint8_t)mode, (uint8_t)relu, (int16_t)save_layer, (uint16_t)ncols, (uint16_t)(bias_row * 256), save_bytes};
+    void epi(int mode, int relu, int save_layer, int mask_layer, int ncols, int bias_row, uint32_t save_bytes, int signal = 1) {
+        P.epis[P.n_epis++] = Epi{(uint8_t)mode, (uint8_t)relu, (int8_t)save_layer, (int8_t)mask_layer, (uint16_t)ncols,
+                                 (uint16_t)(bias_row * 256), save_bytes, (uint32_t)signal};
     }
     // the encoded xyz part (K = 96) of layers 0 and 5: A operand from the item image, 3 weight stages
     void xyz_part(int p, bool first_layer) {
@@ -387,69 +530,97 @@ struct Builder {
         for (int c = 0; c < 3; ++c) w[c] = load_w(16384, PK_FWD, p, 256, 32 * c);
         for (int T = 0; T < 2; ++T)
             for (int c = 0; c < 3; ++c) {
-                const int a_slot = c < 2 ? (T == 0 ? x0 : x1) : x2;
+                const int a_seq = c < 2 ? (T == 0 ? x0 : x1) : x2;
                 const uint32_t a_off = c < 2 ? c * 8192u : T * 8192u;
-                int flags = F_A_SLOT;
+                int flags = 0;
                 if (first_layer && c == 0) flags |= F_FIRST | F_WAIT_PREV;
                 if (c == 2) flags |= F_COMMIT_ACC;
                 int rel0 = -1, rel1 = -1;
                 if (T == 0) { if (c == 1) rel0 = x0; }
                 else { rel0 = w[c]; if (c == 1) rel1 = x1; if (c == 2) rel1 = x2; }
-                mma(T, flags, 2, 0, a_slot, a_off, w[c], 0, rel0, rel1);
+                mma(T, flags, 2, 256, a_seq, a_off, w[c], 0, rel0, rel1);
             }
     }
     // a K = 256 accumulation over the act buffer (8 stages), tiles interleaved half a layer apart
-    void h_part(int p, int k0, bool commit) {
+    void h_part(uint16_t kind, int p, int k0, int n0, bool commit) {
         int w[8];
-        for (int c = 0; c < 8; ++c) w[c] = load_w(16384, PK_FWD, p, 256, k0 + 32 * c);
+        for (int c = 0; c < 8; ++c) w[c] = load_w(16384, kind, p, 256, k0 + 32 * c, n0);
         for (int h = 0; h < 2; ++h)
             for (int T = 0; T < 2; ++T)
                 for (int c = 4 * h; c < 4 * h + 4; ++c) {
                     int flags = 0;
                     if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
                     if (c == 7 && commit) flags |= F_COMMIT_ACC;
-                    mma(T, flags, 2, 0, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
+                    mma(T, flags, 2, 256, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
                 }
+    }
+    // pad the stage count to a multiple of the ring size (static slot indices), resolve the op table
+    bool finish(char* why, size_t n) {
+        std::vector<int> dummies;
+        while (seq % kSlots) {
+            P.loads[P.n_loads++] = Load{LOAD_W, 0, 16};
+            dummies.push_back(seq++);
+        }
+        for (size_t i = 0; i < dummies.size(); i += 2)
+            mma(0, 0, 0, 256, -1, 0, dummies[i], 0, dummies[i], i + 1 < dummies.size() ? dummies[i + 1] : -1);
+        if (P.n_loads > kMaxLoads || (int)ops.size() > kMaxMmas) { snprintf(why, n, "program too large"); return false; }
+        int ready = 0;
+        bool released[kMaxLoads] = {};
+        for (size_t i = 0; i < ops.size(); ++i) {
+            const RawMma& o = ops[i];
+            int hi = std::max(o.a_seq, o.b_seq);
+            if (o.rel1 > hi && o.nk16 == 0) hi = o.rel1;
+            // every stage <= hi - kSlots must have been released by earlier groups, else the producer
+            // (which refills slots in order) and the issuer deadlock
+            for (int s = 0; s <= hi - kSlots; ++s)
+                if (!released[s]) { snprintf(why, n, "mma group %zu needs stage %d but stage %d is still held", i, hi, s); return false; }
+            Mma m{};
+            const uint32_t a_byte = o.a_seq >= 0 ? kRingOff + (uint32_t)(o.a_seq % kSlots) * kSlotBytes + o.a_off
+                                                 : (uint32_t)o.tile * kActBytes + o.a_off;
+            const uint32_t b_byte = kRingOff + (uint32_t)((o.b_seq < 0 ? 0 : o.b_seq) % kSlots) * kSlotBytes + o.b_off;
+            m.a_lo = a_byte >> 4;
+            m.b_lo = b_byte >> 4;
+            m.a_hi = o.a_seq >= 0 ? kHi64 : kHi128;
+            m.b_hi = kHi64;
+            m.idesc = tc::idesc_bf16(128, o.n, 0, 0);
+            m.d_col = (uint16_t)(o.tile * 256);
+            m.nk16 = (uint8_t)o.nk16;
+            m.flags = (uint8_t)o.flags;
+            m.tile = (uint8_t)o.tile;
+            m.n_wait = (uint8_t)std::max(0, hi + 1 - ready);
+            ready = std::max(ready, hi + 1);
+            m.rel0 = o.rel0 >= 0 ? (uint8_t)(o.rel0 % kSlots) : 0xFF;
+            m.rel1 = o.rel1 >= 0 ? (uint8_t)(o.rel1 % kSlots) : 0xFF;
+            if (o.rel0 >= 0) released[o.rel0] = true;
+            if (o.rel1 >= 0) released[o.rel1] = true;
+            P.mmas[P.n_mmas++] = m;
+        }
+        if (ready != seq) { snprintf(why, n, "%d stages loaded but %d consumed", seq, ready); return false; }
+        for (int s = 0; s < seq; ++s)
+            if (!released[s]) { snprintf(why, n, "stage %d is never released", s); return false; }
+        return true;
     }
 };
 
-// every ring slot an MMA group needs must be loadable: all sequence numbers <= need - kSlots have to
-// be released by earlier groups, else producer and issuer deadlock.
-bool validate(const Program& P, char* why, size_t n) {
-    bool released[kMaxLoads] = {};
-    for (int i = 0; i < P.n_mmas; ++i) {
-        const Mma& op = P.mmas[i];
-        int hi = op.b_slot;
-        if ((op.flags & F_A_SLOT) && op.a_slot > hi) hi = op.a_slot;
-        for (int s = 0; s <= hi - kSlots; ++s)
-            if (!released[s]) { snprintf(why, n, "mma group %d needs slot seq %d but seq %d is still held", i, hi, s); return false; }
-        if (op.rel0 >= 0) released[op.rel0] = true;
-        if (op.rel1 >= 0) released[op.rel1] = true;
-    }
-    for (int s = 0; s < P.n_loads; ++s)
-        if (!released[s]) { snprintf(why, n, "slot seq %d is never released", s); return false; }
-    return true;
-}
-
 struct Programs {
-    Builder fwd;
+    Builder fwd, bwd;
+    PackTable pack{};
     bool ok = false;
     char why[160] = "";
 };
 
-void build_into(Programs& S) {
-    Builder& b = S.fwd;
+void build_fwd(Builder& b) {
     // layer 0: xyz (96) -> 256
     b.xyz_part(0, true);
-    b.epi(EPI_ACT, 1, 0, 256, 0, kActBytes);
+    b.epi(EPI_ACT, 1, 0, -1, 256, 0, kActBytes);
     for (int l = 1; l <= 8; ++l) {          // layers_xyz.1-7 and fc_feat (l == 8, no activation)
         if (l == 5) {                       // cat(xyz, h): weight columns 0..95 = xyz, 96..351 = h
-            b.h_part(5, 96, false);
+            b.h_part(PK_FWD, 5, 96, 0, false);
             b.xyz_part(5, false);
         } else {
-            b.h_part(l, 0, true);
+            b.h_part(PK_FWD, l, 0, 0, true);
         }
-        b.epi(EPI_ACT, l < 8 ? 1 : 0, l, 256, l, kActBytes);
+        b.epi(EPI_ACT, l < 8 ? 1 : 0, l, -1, 256, l, kActBytes);
     }
     {   // view branch + density: N = 144 = [layers_dir.0 (128) | fc_alpha | 15 x 0], K = 256 feat + 32 dir
         int w[9];
@@ -459,24 +630,57 @@ void build_into(Programs& S) {
         for (int h = 0; h < 2; ++h)
             for (int T = 0; T < 2; ++T) {
                 for (int c = 4 * h; c < 4 * h + 4; ++c)
-                    b.mma(T, c == 0 ? (F_FIRST | F_WAIT_ACT) : 0, 2, 1, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
-                if (h == 1) b.mma(T, F_A_SLOT | F_COMMIT_ACC, 2, 1, d, T * 8192u, w[8], 0, T == 1 ? w[8] : -1, T == 1 ? d : -1);
+                    b.mma(T, c == 0 ? (F_FIRST | F_WAIT_ACT) : 0, 2, 144, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
+                if (h == 1) b.mma(T, F_COMMIT_ACC, 2, 144, d, T * 8192u, w[8], 0, T == 1 ? w[8] : -1, T == 1 ? d : -1);
             }
-        b.epi(EPI_DIR, 1, 9, 144, 9, 32768);
+        b.epi(EPI_DIR, 1, 9, -1, 144, 9, 32768);
     }
     {   // colour (+ mu, sigma) heads: N = 16, K = 128 (the view-branch activations, k-blocks 0..1)
-        const int wl = b.load_w(4096, PK_FWD_HEADS, 11, 16, 0, 4);
+        const int wl = b.load_w(4096, PK_FWD_HEADS, 11, 16, 0, 0, 4);
         for (int T = 0; T < 2; ++T)
             for (int c = 0; c < 4; ++c) {
                 int flags = 0;
                 if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
                 if (c == 3) flags |= F_COMMIT_ACC;
-                b.mma(T, flags, 2, 2, -1, (c / 2) * 16384u + (c % 2) * 64u, wl, c * 1024u, (T == 1 && c == 3) ? wl : -1);
+                b.mma(T, flags, 2, 16, -1, (c / 2) * 16384u + (c % 2) * 64u, wl, c * 1024u, (T == 1 && c == 3) ? wl : -1);
             }
-        b.epi(EPI_OUT, 0, -1, 16, 10, 0);
+        b.epi(EPI_OUT, 0, -1, -1, 16, 10, 0);
     }
-    b.K.total_bytes = b.woff;
-    S.ok = validate(b.P, S.why, sizeof(S.why));
+}
+
+void build_bwd(Builder& b) {
+    // dZ_dir (+ density column) from the output cotangents, on CUDA cores
+    b.epi(EPI_BWD_IN, 0, 9, 9, 144, 0, 49152);
+    {   // dZ_feat = [dZ_dir | g_density | 0] (K = 144) . [W_dir[:, :256] ; w_alpha]
+        int w[5];
+        for (int c = 0; c < 5; ++c) w[c] = b.load_w(16384, PK_BWD_DIR, 10, 256, 32 * c);
+        for (int h = 0; h < 2; ++h)
+            for (int T = 0; T < 2; ++T)
+                for (int c = (h == 0 ? 0 : 3); c < (h == 0 ? 3 : 5); ++c) {
+                    int flags = 0;
+                    if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
+                    if (c == 4) flags |= F_COMMIT_ACC;
+                    b.mma(T, flags, c < 4 ? 2 : 1, 256, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
+                }
+        b.epi(EPI_BWD_MASK, 0, 8, -1, 256, 0, kActBytes);           // fc_feat has no activation
+    }
+    for (int p = 8; p >= 1; --p) {          // dZ_{p-1} = (dZ_p . W_p) * relu'_{p-1}; layer 5 skips its xyz columns
+        b.h_part(PK_BWD, p, 0, p == 5 ? 96 : 0, true);
+        b.epi(EPI_BWD_MASK, 0, p - 1, p - 1, 256, 0, kActBytes, p > 1 ? 1 : 0);
+    }
+}
+
+void build_into(Programs& S) {
+    S.fwd.K = &S.pack;
+    S.bwd.K = &S.pack;
+    build_fwd(S.fwd);
+    if (!S.fwd.finish(S.why, sizeof(S.why))) return;
+    S.bwd.wbase = S.fwd.woff;
+    build_bwd(S.bwd);
+    if (!S.bwd.finish(S.why, sizeof(S.why))) return;
+    if (S.pack.n > kMaxPack) { snprintf(S.why, sizeof(S.why), "pack table too large"); return; }
+    S.pack.total_bytes = S.fwd.woff + S.bwd.woff;
+    S.ok = true;
 }
 
 Programs* build_programs() {            // host tables are built exactly once
@@ -492,11 +696,20 @@ int ensure_programs() {
     std::call_once(g_once, [] {
         g_programs = build_programs();
         if (!g_programs->ok) { g_upload_rc = 1; return; }
-        if (cudaMemcpyToSymbol(c_prog_fwd, &g_programs->fwd.P, sizeof(Program)) != cudaSuccess) g_upload_rc = 2;
-        if (cudaMemcpyToSymbol(c_pack_fwd, &g_programs->fwd.K, sizeof(PackTable)) != cudaSuccess) g_upload_rc = 2;
-        if (cudaFuncSetAttribute(mlp_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+        if (cudaMemcpyToSymbol(c_prog, &g_programs->fwd.P, sizeof(Program), 0) != cudaSuccess) g_upload_rc = 2;
+        if (cudaMemcpyToSymbol(c_prog, &g_programs->bwd.P, sizeof(Program), sizeof(Program)) != cudaSuccess) g_upload_rc = 2;
+        if (cudaMemcpyToSymbol(c_pack, &g_programs->pack, sizeof(PackTable)) != cudaSuccess) g_upload_rc = 2;
+        if (cudaFuncSetAttribute(mlp_tc_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+        if (cudaFuncSetAttribute(mlp_tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
     });
     return g_upload_rc;
+}
+
+int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
 }
 
 }  // namespace
@@ -512,13 +725,18 @@ using namespace ddnerf;
     } while (0)
 
 extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_wimg_bytes(void) {
-    return build_programs()->fwd.woff;
+    Programs* S = build_programs();
+    return (int64_t)S->fwd.woff + S->bwd.woff;
 }
-extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_bias_floats(void) { return 11 * 256; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_bias_floats(void) { return tcmlp::kBiasRows * 256; }
 extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_items(int64_t rows) { return (rows + tcmlp::kItemRows - 1) / tcmlp::kItemRows; }
 extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_enc_bytes(int64_t rows) { return ddnerf_mlp_tc_items(rows) * tcmlp::kEncItemBytes; }
-extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_act_save_bytes(int64_t rows) { return 10 * ddnerf_mlp_tc_items(rows) * 2 * (int64_t)tcmlp::kActBytes; }
-extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_mask_save_bytes(int64_t rows) { return 10 * ddnerf_mlp_tc_items(rows) * 2 * 128 * 32; }
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_act_save_bytes(int64_t rows) {
+    return tcmlp::kSaveLayers * ddnerf_mlp_tc_items(rows) * 2 * (int64_t)tcmlp::kActBytes;
+}
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_mask_save_bytes(int64_t rows) {
+    return tcmlp::kSaveLayers * ddnerf_mlp_tc_items(rows) * 2 * 128 * 32;
+}
 
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_pack(const ddnerf_mlp_params* p, int out_channels, void* wimg, float* bias_pack,
                                                 void* stream) {
@@ -528,8 +746,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_pack(const ddnerf_mlp_params* p, int 
     TC_ENSURE("mlp_tc_pack");
     PackArgs a{*p, static_cast<uint8_t*>(wimg), bias_pack, out_channels};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    pack_weights_kernel<<<g_programs->fwd.K.n, 256, 0, st>>>(a);
-    pack_bias_kernel<<<11, 256, 0, st>>>(a);
+    pack_weights_kernel<<<g_programs->pack.n, 256, 0, st>>>(a);
+    pack_bias_kernel<<<kBiasRows, 256, 0, st>>>(a);
     DDNERF_LAUNCHED("mlp_tc_pack", 2);
     return 0;
 }
@@ -550,18 +768,49 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float
                                                    int out_channels, float* out, void* act_save, void* mask_save, void* stream) {
     DDNERF_CHECK_ARG(wimg && bias_pack && enc_img && out, "mlp_tc_forward: null pointer");
     DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_forward: out_channels=%d (4 or 6)", out_channels);
+    DDNERF_CHECK_ARG((act_save == nullptr) == (mask_save == nullptr), "mlp_tc_forward: act_save and mask_save go together");
     DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_forward: the bf16 MLP needs an sm_100 device (tcgen05)");
     if (rows == 0) return 0;
     TC_ENSURE("mlp_tc_forward");
     const int64_t n_items = ddnerf_mlp_tc_items(rows);
     DDNERF_CHECK_ARG(n_items < (1 << 30), "mlp_tc_forward: too many rows");
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ChainArgs g{static_cast<const uint8_t*>(wimg), bias_pack, static_cast<const uint8_t*>(enc_img), out,
-                static_cast<uint8_t*>(act_save), static_cast<uint32_t*>(mask_save), rows, (int)n_items, out_channels};
-    const int grid = (int)std::min<int64_t>(n_items, sms);
-    mlp_tc_chain_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    ChainArgs g{};
+    g.wimg = static_cast<const uint8_t*>(wimg);
+    g.bias = bias_pack;
+    g.enc = static_cast<const uint8_t*>(enc_img);
+    g.out = out;
+    g.save = static_cast<uint8_t*>(act_save);
+    g.mask = static_cast<uint32_t*>(mask_save);
+    g.rows = rows;
+    g.n_items = (int)n_items;
+    g.C = out_channels;
+    const int grid = (int)std::min<int64_t>(n_items, sm_count());
+    mlp_tc_chain_kernel<0><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED("mlp_tc_forward", 1);
+    return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const float* bias_pack, const float* grad_out,
+                                                       int64_t rows, int out_channels, const void* mask_save, void* dz_save,
+                                                       void* stream) {
+    DDNERF_CHECK_ARG(wimg && bias_pack && grad_out && mask_save && dz_save, "mlp_tc_backward_dx: null pointer");
+    DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_backward_dx: out_channels=%d (4 or 6)", out_channels);
+    DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_backward_dx: the bf16 MLP needs an sm_100 device (tcgen05)");
+    if (rows == 0) return 0;
+    TC_ENSURE("mlp_tc_backward_dx");
+    const int64_t n_items = ddnerf_mlp_tc_items(rows);
+    DDNERF_CHECK_ARG(n_items < (1 << 30), "mlp_tc_backward_dx: too many rows");
+    ChainArgs g{};
+    g.wimg = static_cast<const uint8_t*>(wimg) + g_programs->fwd.woff;
+    g.bias = bias_pack;
+    g.gout = grad_out;
+    g.save = static_cast<uint8_t*>(dz_save);
+    g.mask = static_cast<uint32_t*>(const_cast<void*>(mask_save));
+    g.rows = rows;
+    g.n_items = (int)n_items;
+    g.C = out_channels;
+    const int grid = (int)std::min<int64_t>(n_items, sm_count());
+    mlp_tc_chain_kernel<1><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    DDNERF_LAUNCHED("mlp_tc_backward_dx", 1);
     return 0;
 }

@@ -46,6 +46,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// raw shared-address variants (the MMA issuer keeps barrier addresses as 32-bit integers)
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+#ifdef DDNERF_TC_WATCHDOG
+    uint32_t spins = 0;
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (++spins > (1u << 26)) { printf("ddnerf tc: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+#else
+    while (!mbar_try_wait_u32(bar, parity)) {}
+#endif
+}
+// true in exactly one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk stores)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -91,9 +124,10 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 }
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) { mma_commit_u32(smem_u32(bar)); }
 
 // TMEM -> registers: lane = threadIdx%32 of the warp's lane quarter, 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

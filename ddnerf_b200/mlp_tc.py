@@ -72,8 +72,59 @@ def forward_only(module, rays, t_vals, ray_shape="cone"):
     return out
 
 
+class _MlpTc(torch.autograd.Function):
+    """Training path: forward keeps every layer's bf16 activations (tile images) and ReLU masks;
+    backward = dX chain kernel + weight-gradient kernel.  No gradient flows to rays / t_vals (the
+    reference's sampler output is a detached leaf, models.py:227-237)."""
+
+    @staticmethod
+    def forward(ctx, module, rays, t_vals, ray_shape, *params):
+        lib = _lib.load()
+        st = _state(module)
+        st.refresh()
+        N, S = rays.shape[0], t_vals.shape[1] - 1
+        rows, C, dev = N * S, module.out_channels, rays.device
+        img = encode_img(rays, t_vals, ray_shape)
+        out = torch.empty(rows, C, device=dev, dtype=torch.float32)
+        act = torch.empty(max(lib.ddnerf_mlp_tc_act_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
+        mask = torch.empty(max(lib.ddnerf_mlp_tc_mask_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
+        with _mlp_timer():
+            _lib.check(lib.ddnerf_mlp_tc_forward(_p(st.wimg), _p(st.bias), _p(img), rows, C, _p(out), _p(act), _p(mask),
+                                                 _stream()), "mlp_tc_forward")
+        ctx.st, ctx.img, ctx.act, ctx.mask = st, img, act, mask
+        ctx.rows, ctx.C = rows, C
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        st, rows, C = ctx.st, ctx.rows, ctx.C
+        grad_out = _req(grad_out, "grad_out")
+        dev = grad_out.device
+        nw = len(ctx.shapes) // 2
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        views, off = [], 0
+        for s, n in zip(ctx.shapes, sizes):
+            views.append(flat[off:off + n].view(s))
+            off += n
+        gws, gbs = views[:nw], views[nw:]
+        dz = torch.empty(ctx.act.numel(), device=dev, dtype=torch.uint8)
+        table = _ptr_table(gws, gbs)
+        with _mlp_timer():
+            _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(grad_out), rows, C, _p(ctx.mask), _p(dz),
+                                                     _stream()), "mlp_tc_backward_dx")
+            _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(ctx.act), _p(dz), _p(ctx.img), _p(grad_out), ctypes.byref(table), rows, C,
+                                                     _stream()), "mlp_tc_backward_dw")
+        ctx.img = ctx.act = ctx.mask = None
+        return (None, None, None, None, *views)
+
+
 def mlp_bf16(module, rays, t_vals, ray_shape="cone"):
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
-    if needs_grad:
-        raise NotImplementedError("bf16 MLP backward is not wired yet")
-    return forward_only(module, rays, t_vals, ray_shape)
+    if not needs_grad:
+        return forward_only(module, rays, t_vals, ray_shape)
+    pairs = module._param_pairs()
+    rays, t_vals = _req(rays, "rays"), _req(t_vals.detach(), "t_vals")
+    return _MlpTc.apply(module, rays, t_vals, ray_shape, *[w for w, _ in pairs], *[b for _, b in pairs])

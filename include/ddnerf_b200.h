@@ -120,6 +120,19 @@ int ddnerf_mlp_tc_forward(const void* wimg, const float* bias_pack, const void* 
                           int64_t rows, int out_channels, float* out, void* act_save,
                           void* mask_save, void* stream);
 
+/* Backward of the bf16 MLP (autograd of base_architectures.py:40-61 / 103-126), two kernels:
+ * (1) the dX chain: grad_out [rows,C] -> dZ tile images of every layer (dz_save, same size and
+ *     format as act_save), using the ReLU masks the training forward stored;
+ * (2) the weight/bias gradients dW_l = dZ_l^T . A_{l-1}, db_l = colsum(dZ_l), ACCUMULATED with fp32
+ *     atomics into `grads` (caller zeroes the buffers; [out,in] nn.Linear layout, any 4-byte
+ *     alignment).  No gradient is produced for the encoded inputs (nothing upstream is trainable). */
+int ddnerf_mlp_tc_backward_dx(const void* wimg, const float* bias_pack, const float* grad_out,
+                              int64_t rows, int out_channels, const void* mask_save,
+                              void* dz_save, void* stream);
+int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const void* enc_img,
+                              const float* grad_out, const ddnerf_mlp_grads* grads, int64_t rows,
+                              int out_channels, void* stream);
+
 /* Descriptor self-test of the tcgen05 path (test infrastructure of the bf16 MLP): one CTA computes
  * D[128,N] = A.B^T from two operand tile images given in their shared-memory byte layout, with the
  * shared-memory descriptors (start address 0), instruction descriptor and per-k16-step address

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the fused bf16 MLP kernels (CUDA events, after warm-up).
+
+    python tools/bench_mlp_tc.py [--rows 1048576] [--iters 10]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=8192)
+    ap.add_argument("--samples", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--save", action="store_true", help="training forward (store activations + masks)")
+    args = ap.parse_args()
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200 import _lib, mlp_tc
+    from ddnerf_b200.models import base_architectures as BA
+    from ddnerf_b200.ops import _p, _stream
+    from ddnerf_b200.rays import synth_rays
+    lib = _lib.load()
+    N, S = args.rays, args.samples
+    ro, rd, rad, near, far = synth_rays("blender", N, seed=1)
+    rays = orc.pack_rays(ro, rd, rad, near, far).cuda()
+    t_vals = orc.sample_first_cycle(rays[:, 7:8].cpu(), rays[:, 8:9].cpu(), S).cuda()
+    net = BA.MipNeRFModel(hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True)
+    net.to("cuda")
+    st = mlp_tc._state(net)
+    st.refresh()
+    rows = N * S
+    out = torch.empty(rows, 4, device="cuda")
+    act = mask = None
+    if args.save:
+        act = torch.empty(lib.ddnerf_mlp_tc_act_save_bytes(rows), device="cuda", dtype=torch.uint8)
+        mask = torch.empty(lib.ddnerf_mlp_tc_mask_save_bytes(rows), device="cuda", dtype=torch.uint8)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    res = {}
+    for name, fn in (("encode", lambda: mlp_tc.encode_img(rays, t_vals)),):
+        for _ in range(3):
+            img = fn()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.iters):
+            img = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name + "_ms"] = e0.elapsed_time(e1) / args.iters
+
+    def fwd():
+        _lib.check(lib.ddnerf_mlp_tc_forward(_p(st.wimg), _p(st.bias), _p(img), rows, 4, _p(out), _p(act), _p(mask), _stream()), "fwd")
+
+    for _ in range(3):
+        fwd()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.iters):
+        fwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    flops = 2.0 * 610304 * rows
+    res.update(rows=rows, fwd_ms=ms, fwd_tflops=flops / ms / 1e9, save=bool(args.save))
+    if args.save:
+        dz = torch.empty_like(act)
+        gout = torch.randn(rows, 4, device="cuda")
+        pairs = net._param_pairs()
+        gws = [torch.zeros_like(w) for w, _ in pairs]
+        gbs = [torch.zeros_like(b) for _, b in pairs]
+        from ddnerf_b200.ops import _ptr_table
+        table = _ptr_table(gws, gbs)
+
+        def dx():
+            _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(gout), rows, 4, _p(mask), _p(dz), _stream()), "dx")
+
+        def dw():
+            _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(act), _p(dz), _p(img), _p(gout), ctypes.byref(table), rows, 4, _stream()), "dw")
+
+        for name, fn, macs in (("dx", dx, 557696), ("dw", dw, 610304)):
+            for _ in range(2):
+                fn()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(args.iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            res[name + "_ms"] = ms
+            res[name + "_tflops"] = 2.0 * macs * rows / ms / 1e9
+        res["dw_gbs"] = (2 * act.numel()) / res["dw_ms"] / 1e6
+        tot = res["fwd_ms"] + res["dx_ms"] + res["dw_ms"]
+        res["train_tflops"] = 2.0 * (610304 * 2 + 557696) * rows / tot / 1e9
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
