@@ -724,6 +724,12 @@ using namespace ddnerf;
         DDNERF_CHECK_ARG(rc__ == 0, "%s: device setup failed (%d): %s", who, rc__, cudaGetErrorString(cudaGetLastError())); \
     } while (0)
 
+/* 0 when the static kernel programs (ring schedule, op tables) are consistent; host-only check */
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_program_check(void) {
+    Programs* S = build_programs();
+    DDNERF_CHECK_ARG(S->ok, "mlp_tc: invalid kernel program: %s", S->why);
+    return 0;
+}
 extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_wimg_bytes(void) {
     Programs* S = build_programs();
     return (int64_t)S->fwd.woff + S->bwd.woff;

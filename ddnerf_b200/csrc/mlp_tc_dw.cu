@@ -273,6 +273,38 @@ __global__ void __launch_bounds__(kDwThreads, 1) mlp_tc_dw_kernel(const DwArgs g
     if (warp == 1) tc::tmem_dealloc(ctl->tmem_base, 512);
 }
 
+// Split the SMs over the layer-ops in proportion to their bytes per tile; each CTA then takes a
+// contiguous tile range of its op.  Every (op, tile) pair is covered exactly once.
+int plan_work(uint32_t n_tiles, int sms, DwWork& work) {
+    sms = std::max(kNumOps, std::min(sms, kMaxWork));
+    uint32_t wsum = 0;
+    for (int o = 0; o < kNumOps; ++o) wsum += h_op_weight[o];
+    int cnt[kNumOps], total = 0;
+    for (int o = 0; o < kNumOps; ++o) {
+        cnt[o] = std::max(1, (int)((uint64_t)sms * h_op_weight[o] / wsum));
+        cnt[o] = (int)std::min<uint32_t>((uint32_t)cnt[o], n_tiles);
+        total += cnt[o];
+    }
+    while (total != sms) {                  // give to the most loaded / take from the least loaded op
+        int best = -1;
+        for (int o = 0; o < kNumOps; ++o) {
+            if (total < sms ? (uint32_t)cnt[o] >= n_tiles : cnt[o] <= 1) continue;
+            if (best < 0) { best = o; continue; }
+            const uint64_t lo = (uint64_t)h_op_weight[o] * cnt[best], lb = (uint64_t)h_op_weight[best] * cnt[o];
+            if (total < sms ? lo > lb : lo < lb) best = o;
+        }
+        if (best < 0) break;
+        if (total < sms) { ++cnt[best]; ++total; } else { --cnt[best]; --total; }
+    }
+    int n_work = 0;
+    for (int o = 0; o < kNumOps; ++o)
+        for (int j = 0; j < cnt[o]; ++j) {
+            const uint32_t t0 = (uint32_t)((uint64_t)n_tiles * j / cnt[o]), t1 = (uint32_t)((uint64_t)n_tiles * (j + 1) / cnt[o]);
+            if (t1 > t0 && n_work < kMaxWork) work.w[n_work++] = WorkItem{(uint32_t)o, t0, t1};
+        }
+    return n_work;
+}
+
 std::once_flag g_dw_once;
 int g_dw_rc = 0;
 
@@ -300,36 +332,9 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    sms = std::min(sms, kMaxWork);
 
-    // split the SMs over the layer-ops in proportion to their bytes per tile; each CTA then takes a
-    // contiguous tile range of its op
-    uint32_t wsum = 0;
-    for (int o = 0; o < kNumOps; ++o) wsum += h_op_weight[o];
-    int cnt[kNumOps], total = 0;
-    for (int o = 0; o < kNumOps; ++o) {
-        cnt[o] = std::max(1, (int)((uint64_t)sms * h_op_weight[o] / wsum));
-        cnt[o] = (int)std::min<uint32_t>((uint32_t)cnt[o], n_tiles);
-        total += cnt[o];
-    }
-    while (total != sms) {                  // give to the most loaded / take from the least loaded op
-        int best = -1;
-        for (int o = 0; o < kNumOps; ++o) {
-            if (total < sms ? (uint32_t)cnt[o] >= n_tiles : cnt[o] <= 1) continue;
-            if (best < 0) { best = o; continue; }
-            const uint64_t lo = (uint64_t)h_op_weight[o] * cnt[best], lb = (uint64_t)h_op_weight[best] * cnt[o];
-            if (total < sms ? lo > lb : lo < lb) best = o;
-        }
-        if (best < 0) break;
-        if (total < sms) { ++cnt[best]; ++total; } else { --cnt[best]; --total; }
-    }
     DwWork work{};
-    int n_work = 0;
-    for (int o = 0; o < kNumOps; ++o)
-        for (int j = 0; j < cnt[o]; ++j) {
-            const uint32_t t0 = (uint32_t)((uint64_t)n_tiles * j / cnt[o]), t1 = (uint32_t)((uint64_t)n_tiles * (j + 1) / cnt[o]);
-            if (t1 > t0 && n_work < kMaxWork) work.w[n_work++] = WorkItem{(uint32_t)o, t0, t1};
-        }
+    const int n_work = plan_work(n_tiles, sms, work);
     DwArgs g{};
     g.act = static_cast<const uint8_t*>(act_save);
     g.dz = static_cast<const uint8_t*>(dz_save);
@@ -343,4 +348,18 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
     mlp_tc_dw_kernel<<<n_work, kDwThreads, kDwSmemBytes, static_cast<cudaStream_t>(stream)>>>(g, work);
     DDNERF_LAUNCHED("mlp_tc_backward_dw", 1);
     return 0;
+}
+
+/* host-side work split of ddnerf_mlp_tc_backward_dw for `rows` sample rows on `sms` SMs: writes
+ * (op, first tile, end tile) triples, returns their number (test hook, no device work) */
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_dw_plan(int64_t rows, int sms, uint32_t* triples, int max_items) {
+    DDNERF_CHECK_ARG(triples && rows >= 0 && sms > 0, "mlp_tc_dw_plan: bad arguments");
+    DwWork work{};
+    const int n = rows == 0 ? 0 : plan_work((uint32_t)(ddnerf_mlp_tc_items(rows) * 2), sms, work);
+    for (int i = 0; i < n && i < max_items; ++i) {
+        triples[3 * i] = work.w[i].op;
+        triples[3 * i + 1] = work.w[i].t0;
+        triples[3 * i + 2] = work.w[i].t1;
+    }
+    return n;
 }

@@ -30,6 +30,7 @@ class FlatBucket:
     """All parameters of one network as views into one contiguous fp32 buffer + Adam state."""
 
     def __init__(self, module):
+        self.module = module
         self.params = [p for p in module.parameters()]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -55,6 +56,27 @@ class FlatBucket:
     def adam(self, lr, grad_scale=1.0):
         self.step += 1
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step, grad_scale=grad_scale)
+        # the kernel writes through raw pointers (no autograd version bump): tell the bf16 path that its
+        # packed weight images are stale
+        st = getattr(self.module, "_tc_state", None)
+        if st is not None:
+            st.dirty = True
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous pixel-row range [lo, hi) of one rank when a frame of `n_rows` image rows is rendered
+    by `world` ranks (rendering splits rows, no collective)."""
+    lo = (n_rows * rank) // world
+    hi = (n_rows * (rank + 1)) // world
+    return lo, hi
+
+
+def allreduce_gradients(buckets, world):
+    """The one collective of a data-parallel step: sum every flat gradient bucket across ranks (NCCL
+    on GPUs, gloo in the CPU tests).  The 1/world factor is applied by the optimizer kernel."""
+    if world > 1:
+        for b in buckets:
+            dist.all_reduce(b.grad, op=dist.ReduceOp.SUM)
 
 
 class Trainer:
@@ -104,8 +126,8 @@ class Trainer:
         lr = self.lr(i)
         for b in self.buckets:
             b.gather_grads()
-            if self.distributed and self.world > 1:
-                dist.all_reduce(b.grad, op=dist.ReduceOp.SUM)
+        allreduce_gradients(self.buckets, self.world if self.distributed else 1)
+        for b in self.buckets:
             b.adam(lr, grad_scale=1.0 / self.world)
         self.iter += 1
         return loss, mse

@@ -133,6 +133,12 @@ int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const v
                               const float* grad_out, const ddnerf_mlp_grads* grads, int64_t rows,
                               int out_channels, void* stream);
 
+/* Host-only consistency hooks (no device work): the static ring/op programs of the chain kernels
+ * (0 = consistent) and the (layer-op, tile range) split of backward_dw over `sms` SMs, written as
+ * (op, first tile, end tile) uint32 triples; returns the number of work items. */
+int ddnerf_mlp_tc_program_check(void);
+int ddnerf_mlp_tc_dw_plan(int64_t rows, int sms, uint32_t* triples, int max_items);
+
 /* Descriptor self-test of the tcgen05 path (test infrastructure of the bf16 MLP): one CTA computes
  * D[128,N] = A.B^T from two operand tile images given in their shared-memory byte layout, with the
  * shared-memory descriptors (start address 0), instruction descriptor and per-k16-step address
