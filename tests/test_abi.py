@@ -69,3 +69,26 @@ def test_dw_work_split_covers_every_tile_once(rows, sms):
         assert t1 > t0
         cover[op, t0:t1] += 1
     assert (cover == 1).all()
+
+
+def test_install_as_reference_aliases_the_driver_imports():
+    """The reference's drivers do `from models import models` and `from general_utils import CfgNode`
+    (train_model.py:4,14; eval_nerf.py:6,10): after install_as_reference() those names are this package."""
+    import subprocess
+    import sys
+    code = (
+        "import ddnerf_b200; ddnerf_b200.install_as_reference()\n"
+        "from models import models\n"
+        "from models.samplers import sample_pdf_with_mu_sigma\n"
+        "from general_utils import CfgNode, mse2psnr, volume_render_radiance_field\n"
+        "from general_utils.nerf_helpers import positional_encoding, get_minibatches\n"
+        "assert models.DDNerfModel.__module__ == 'ddnerf_b200.models.models'\n"
+        "assert volume_render_radiance_field.__module__ == 'ddnerf_b200.general_utils.volume_rendering_utils'\n"
+        "from ddnerf_b200.config import preset\n"
+        "cfg, _ = preset('config_blender')\n"
+        "m = getattr(models, cfg.nerf.type)(cfg)\n"
+        "names = [k for k, _ in m.coarse.named_parameters()]\n"
+        "assert names[0] == 'layers_xyz.0.weight' and 'fc_mu_sigma.bias' in names and len(names) == 26\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REPO, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
