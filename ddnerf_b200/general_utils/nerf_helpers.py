@@ -50,3 +50,27 @@ def positional_encoding(tensor, num_encoding_functions=6, include_input=True, lo
 
 def get_embedding_function(num_encoding_functions=6, include_input=True, log_sampling=True):
     return lambda x: positional_encoding(x, num_encoding_functions, include_input, log_sampling)
+
+
+def meshgrid_xy(tensor1, tensor2):
+    """nerf_helpers.py:27-40: np.meshgrid(..., indexing="xy")."""
+    ii, jj = torch.meshgrid(tensor1, tensor2, indexing="ij")
+    return ii.transpose(-1, -2), jj.transpose(-1, -2)
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """nerf_helpers.py:182-208 (unused by the shipped drivers, kept for API completeness): shift the
+    origins to the near plane, then the perspective projection to normalised device coordinates."""
+    from ..rays import ndc_project
+    return ndc_project(H, W, focal, near, rays_o, rays_d)
+
+
+def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
+    """nerf_helpers.py:211-245: log-linear interpolation lr_init -> lr_final with an optional sinusoidal
+    warm-up over the first lr_delay_steps (host scalar math of the driver loop)."""
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    else:
+        delay_rate = 1.0
+    t = min(max(step / max_steps, 0), 1)
+    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)

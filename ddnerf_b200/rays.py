@@ -50,18 +50,23 @@ def get_ray_bundle(height, width, focal, c2w):
     return ro, rd, radii
 
 
-def ndc_mipnerf_rays(H, W, focal, rays_o, rays_d, near=1):
-    """dataset_helpers.py:3-42: forward-facing NDC rays + radii from neighbouring origins."""
+def ndc_project(H, W, focal, near, rays_o, rays_d):
+    """The NDC projection shared by nerf_helpers.py:182-208 (ndc_rays) and dataset_helpers.py:3-42:
+    origins moved to the near plane, then x/z, y/z scaled by the focal length, z -> 1 + 2 near / z."""
     t = -(near + rays_o[..., 2]) / rays_d[..., 2]
     rays_o = rays_o + t[..., None] * rays_d
-    o0 = -1.0 / (W / (2.0 * focal)) * rays_o[..., 0] / rays_o[..., 2]
-    o1 = -1.0 / (H / (2.0 * focal)) * rays_o[..., 1] / rays_o[..., 2]
-    o2 = 1.0 + 2.0 * near / rays_o[..., 2]
-    d0 = -1.0 / (W / (2.0 * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
-    d1 = -1.0 / (H / (2.0 * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
-    d2 = -2.0 * near / rays_o[..., 2]
-    o = torch.stack([o0, o1, o2], -1)
-    d = torch.stack([d0, d1, d2], -1)
+    sx, sy = -1.0 / (W / (2.0 * focal)), -1.0 / (H / (2.0 * focal))
+    oz = rays_o[..., 2]
+    ox_z, oy_z = rays_o[..., 0] / oz, rays_o[..., 1] / oz
+    o = torch.stack([sx * ox_z, sy * oy_z, 1.0 + 2.0 * near / oz], -1)
+    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - ox_z), sy * (rays_d[..., 1] / rays_d[..., 2] - oy_z),
+                     -2.0 * near / oz], -1)
+    return o, d
+
+
+def ndc_mipnerf_rays(H, W, focal, rays_o, rays_d, near=1):
+    """dataset_helpers.py:3-42: forward-facing NDC rays + radii from neighbouring origins."""
+    o, d = ndc_project(H, W, focal, near, rays_o, rays_d)
     dx = torch.sqrt(torch.sum((o[:-1] - o[1:]) ** 2, -1))
     dx = torch.cat([dx, dx[-2:-1]])
     dy = torch.sqrt(torch.sum((o[:, :-1] - o[:, 1:]) ** 2, -1))

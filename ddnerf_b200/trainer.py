@@ -14,16 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-
-
-def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1):
-    """general_utils/nerf_helpers.py:211-245."""
-    if lr_delay_steps > 0:
-        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
-    else:
-        delay_rate = 1.0
-    t = min(max(step / max_steps, 0), 1)
-    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+from .general_utils.nerf_helpers import learning_rate_decay  # noqa: F401  (re-exported)
 
 
 class FlatBucket:
