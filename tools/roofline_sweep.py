@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Stage-level roofline report of the HBM-bound kernels (BASELINE.json configs[4]: ray-batch sweep
+4K-64K rays/GPU x 64-256 samples/ray, DDNeRF vs mip-NeRF sampler).
+
+For every (rays, samples per pass) point each kernel is timed alone with CUDA events after warm-up
+(inputs > L2 at the large points; an L2 flush buffer is written between repetitions otherwise) and its
+ALGORITHMIC bytes (stated per kernel below) are divided by the time:
+
+    python tools/roofline_sweep.py [--out profiles/r01_stage_roofline] [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def timed(fn, flush, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        if flush is not None:
+            flush.add_(1.0)                       # evict L2 (buffer larger than the 126 MB L2)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2]                       # median, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/stage_roofline")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    from oracle import ddnerf_oracle as orc           # ray packing only (test infrastructure, not timed)
+    from ddnerf_b200 import mlp_tc, ops
+    from ddnerf_b200.rays import synth_rays
+    peak = 6471.1
+    pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    dev = torch.device("cuda:0")
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)                 # 256 MB
+    rays_list = [4096, 16384, 65536] if args.quick else [4096, 8192, 16384, 32768, 65536]
+    samp_list = [32, 128] if args.quick else [32, 64, 128]
+    rows = []
+    for N in rays_list:
+        ro, rd, rad, near, far = synth_rays("blender", N, seed=2)
+        rays = orc.pack_rays(ro, rd, rad, near, far).to(dev)
+        for S in samp_list:
+            g = torch.Generator(device=dev).manual_seed(1)
+            t0 = ops.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], S, False, torch.rand(N, S + 1, device=dev, generator=g))
+            raw = torch.randn(N, S, 4, device=dev, generator=g)
+            raw6 = torch.randn(N, S, 6, device=dev, generator=g)
+            noise = torch.randn(N, S, device=dev, generator=g)
+            mus = torch.rand(N, S, device=dev, generator=g)
+            sig = torch.rand(N, S, device=dev, generator=g) * 0.5 + 1e-3
+            lt = 0.5 * (1 + torch.erf((0 - mus) / sig / 2 ** 0.5))
+            pin = 0.5 * (1 + torch.erf((1 - mus) / sig / 2 ** 0.5)) - lt
+            u = torch.rand(N, S + 1, device=dev, generator=g)
+            w = ops.composite(raw, t0, rays[:, 3:6], noise, 1.0, None, False, True, False)[3]
+            t1 = ops.sample_pdf_mu_sigma(t0, w, mus, sig, pin, lt, S + 1, True, near, far, u)
+            w1 = ops.composite(raw, t1, rays[:, 3:6], noise, 1.0, None, False, True, False)[3]
+            rawg = raw.clone().requires_grad_(True)
+            out = ops.composite(rawg, t0, rays[:, 3:6], noise, 1.0, None, False, True, False)
+            g_rgb, g_w = torch.randn(N, 3, device=dev, generator=g), torch.randn(N, S, device=dev, generator=g)
+            w0g, mug, sgg = w.clone().requires_grad_(True), mus.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+            dpl = ops.dp_loss(t1, t0, w1, w0g, mug, sgg, lt, pin, False)
+            R = N * S
+            # name, callable, algorithmic bytes
+            stages = [
+                ("first_cycle", lambda: ops.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], S, False, u), 8 * N * (S + 1) + 8 * N),
+                ("sample_pdf (mip-NeRF)", lambda: ops.sample_pdf(t0, w, S + 1, True, u), 4 * N * (4 * S + 3)),
+                ("sample_pdf_mu_sigma (DDNeRF)", lambda: ops.sample_pdf_mu_sigma(t0, w, mus, sig, pin, lt, S + 1, True, near, far, u),
+                 4 * N * (8 * S + 3)),
+                ("composite fwd", lambda: ops.composite(raw, t0, rays[:, 3:6], noise, 1.0, None, False, True, False),
+                 R * 28 + N * (12 + 28)),
+                ("composite fwd (DDNeRF coarse, +mu, 6-ch raw)", lambda: ops.composite(raw6[..., :4], t0, rays[:, 3:6], noise, 1.0, mus, False, False, False),
+                 R * 32 + N * (12 + 32)),
+                ("composite bwd", lambda: torch.autograd.grad((out[0], out[3]), rawg, (g_rgb, g_w), retain_graph=True),
+                 R * (24 + 4 + 16) + N * (12 + 12)),
+                ("dp_loss fwd", lambda: ops.dp_loss(t1, t0, w1, w, mus, sig, lt, pin, False), R * 32),
+                ("dp_loss bwd", lambda: torch.autograd.grad(dpl, (w0g, mug, sgg), retain_graph=True), R * (32 + 12)),
+                ("encode -> bf16 operand images", lambda: mlp_tc.encode_img(rays, t0), R * (4 + 256) + N * 48),
+            ]
+            fl = flush if R * 28 < 512 * 1024 * 1024 else None
+            for name, fn, nbytes in stages:
+                ms = timed(fn, fl)
+                gbs = nbytes / ms / 1e6
+                rows.append(dict(rays=N, samples=S, kernel=name, ms=ms, bytes=nbytes, gbs=gbs, frac=gbs / peak))
+            del raw, raw6, noise, rawg, out, dpl
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    with open(args.out + ".json", "w") as f:
+        json.dump(dict(peak_gbs=peak, peak_kind="MEASURED_PEAKS.json hbm_gbs", rows=rows), f, indent=1)
+    with open(args.out + ".md", "w") as f:
+        f.write("# Stage roofline sweep (HBM-bound kernels; algorithmic bytes / CUDA-event time, L2 flushed between reps)\n\n")
+        f.write(f"peak = {peak} GB/s (measured copy bandwidth)\n\n| rays | samples | kernel | ms | GB/s | frac |\n|---:|---:|---|---:|---:|---:|\n")
+        for r in rows:
+            f.write(f"| {r['rays']} | {r['samples']} | {r['kernel']} | {r['ms']:.4f} | {r['gbs']:.0f} | {r['frac']:.2f} |\n")
+    best = {}
+    for r in rows:
+        best[r["kernel"]] = max(best.get(r["kernel"], 0), r["frac"])
+    print(json.dumps(best))
+
+
+if __name__ == "__main__":
+    main()
