@@ -52,6 +52,10 @@ struct ChainArgs {
     int n_items, C;
 };
 
+// descriptor high words: K-major SWIZZLE_128B act buffer (SBO = 8 rows x 128 B), SWIZZLE_64B ring stages
+constexpr uint32_t kHi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
+constexpr uint32_t kHi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) >> 32);
+
 struct __align__(16) SmemCtl {
     uint64_t full[kSlots], empty[kSlots], acc_full[2], act_ready[2];
     uint32_t tmem_base, pad[3];
@@ -72,14 +76,17 @@ __device__ __forceinline__ void store_chunk32(uint32_t act_u32, int row, int c0,
         st_shared_v4(base + ((((ch0 + i) ^ (uint32_t)row) & 7u) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
 }
 
-// ---- forward epilogue -----------------------------------------------------------------------
+// ---- epilogues --------------------------------------------------------------------------------
+// The two tiles of a work item finish their layers half a layer apart, so their epilogues never
+// coincide: all 8 epilogue warps serve whichever tile is ready.  Warp w reads TMEM lane quarter
+// w % 4 (rows 32 (w % 4) + lane) and owns column half w / 4 (128 of the 256 accumulator columns).
+// Epilogues run in program order, alternating tiles: (e0,T0) (e0,T1) (e1,T0) ...
+constexpr int kEpiThreads = 256;
+
 // 32 accumulator columns [c0, c0+32) of this thread's row: + bias, optional ReLU, -> bf16, stored as
 // four 16-byte chunks of the act buffer.  Returns the sign bitmask (bit i = value i > 0).
-__device__ __forceinline__ uint32_t epi_chunk32(uint32_t tmem_addr, const float* __restrict__ bias_s, int c0, bool relu,
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const float* __restrict__ bias_s, int c0, bool relu,
                                                 uint32_t act_u32, int row) {
-    uint32_t v[32];
-    tc::tmem_ld32(tmem_addr + c0, v);
-    tc::tmem_ld_wait();
     uint32_t pk[16];
     uint32_t m = 0;
 #pragma unroll
@@ -101,192 +108,216 @@ __device__ __forceinline__ uint32_t epi_chunk32(uint32_t tmem_addr, const float*
 
 __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
     const Program& P = c_prog[0];
-    const int T = warp >> 2, q = warp & 3, row = q * 32 + lane;
-    const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
-    const uint32_t tmem_row = ctl->tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
-    float* bias_s = ctl->bias[T];
-    const int bar_id = 1 + T;
+    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane, tid = warp * 32 + lane;
+    const uint32_t tmem_q = ctl->tmem_base + ((uint32_t)(q * 32) << 16);
     const int n_tiles = g.n_items * 2;
     const int n_epis = P.n_epis;
-    uint32_t acc_phase = 0;
-    bool store_pending = false;
+    uint32_t acc_phase = 0;                  // bit T: parity of acc_full[T]
+    int stores = 0;                          // bulk stores issued by thread 0
+    uint32_t k = 0;                          // running epilogue count: parity selects the bias buffer
 
-    {   // bias of the first epilogue
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(g.bias + P.epis[0].bias_off) + row);
-        bias_s[2 * row] = b0.x;
-        bias_s[2 * row + 1] = b0.y;
-        named_bar(bar_id, 128);
-    }
+    ctl->bias[0][tid] = __ldg(g.bias + P.epis[0].bias_off + tid);          // bias of the first epilogue
+    named_bar(1, kEpiThreads);
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-        const int tile_g = item * 2 + T;
-        const int64_t row_g = (int64_t)tile_g * 128 + row;
-        for (int e = 0; e < n_epis; ++e) {
+        for (int e = 0; e < n_epis; ++e, ++k) {
             const Epi E = P.epis[e];
-            const int en = (e + 1 == n_epis) ? 0 : e + 1;
-            const float2 nb = __ldg(reinterpret_cast<const float2*>(g.bias + P.epis[en].bias_off) + row);
-            tc::mbar_wait(&ctl->acc_full[T], acc_phase);
-            acc_phase ^= 1;
-            tc::tc_fence_after_sync();
-            if (g.save) {                // the previous bulk store of this act buffer must have read it
-                if (row == 0 && store_pending) { tc::bulk_wait_read<0>(); store_pending = false; }
-                named_bar(bar_id, 128);
-            }
-            if (E.mode == EPI_ACT || E.mode == EPI_DIR) {
-                uint32_t mk[8];
-                const int nc = (E.mode == EPI_DIR) ? 128 : 256;
+            const float* bias_s = ctl->bias[k & 1];
+            const float nb = __ldg(g.bias + P.epis[(e + 1 == n_epis) ? 0 : e + 1].bias_off + tid);
+#pragma unroll 1
+            for (int T = 0; T < 2; ++T) {
+                const int tile_g = item * 2 + T;
+                const int64_t row_g = (int64_t)tile_g * 128 + row;
+                const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
+                const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
+                tc::mbar_wait(&ctl->acc_full[T], (acc_phase >> T) & 1u);
+                acc_phase ^= 1u << T;
+                tc::tc_fence_after_sync();
+                if (g.save) {            // this tile's previous bulk store must have finished reading the act buffer
+                    if (tid == 0 && stores >= 2) tc::bulk_wait_read<1>();
+                    named_bar(1, kEpiThreads);
+                }
+                if (E.mode == EPI_ACT || E.mode == EPI_DIR) {
+                    const int nc = (E.mode == EPI_DIR) ? 64 : 128;         // columns of this half
+                    const int cb = hf * nc;
+                    uint32_t mk[4] = {0u, 0u, 0u, 0u};
+                    uint32_t va[32], vb[32];
+                    tc::tmem_ld32(tmem_row + cb, va);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    mk[c] = 0;
-                    if (c * 32 < nc) mk[c] = epi_chunk32(tmem_row, bias_s, c * 32, E.relu != 0, act_u32, row);
-                }
-                if (E.mode == EPI_DIR) {                         // column 128 = density (fc_alpha)
+                    for (int c = 0; c < 4; c += 2) {                       // TMEM loads one chunk ahead of the math
+                        tc::tmem_ld_wait();
+                        if ((c + 1) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
+                        if (c * 32 < nc) mk[c] = epi_chunk32(va, bias_s, cb + c * 32, E.relu != 0, act_u32, row);
+                        tc::tmem_ld_wait();
+                        if ((c + 2) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
+                        if ((c + 1) * 32 < nc) mk[c + 1] = epi_chunk32(vb, bias_s, cb + (c + 1) * 32, E.relu != 0, act_u32, row);
+                    }
+                    if (E.mode == EPI_DIR && hf == 0) {                    // column 128 = density (fc_alpha)
+                        uint32_t v[16];
+                        tc::tmem_ld16(tmem_row + 128, v);
+                        tc::tmem_ld_wait();
+                        if (row_g < g.rows) g.out[row_g * g.C + 3] = __uint_as_float(v[0]) + bias_s[128];
+                    }
+                    if (g.mask && E.save_layer >= 0 && E.relu) {
+                        uint32_t* mp = g.mask + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8;
+                        if (E.mode == EPI_DIR) {                           // words 0..1 / 2..3 of the 128 view-branch columns
+                            *reinterpret_cast<uint2*>(mp + 2 * hf) = make_uint2(mk[0], mk[1]);
+                            if (hf == 1) *reinterpret_cast<uint4*>(mp + 4) = make_uint4(0u, 0u, 0u, 0u);
+                        } else {
+                            *reinterpret_cast<uint4*>(mp + 4 * hf) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+                        }
+                    }
+                } else if (hf == 0) {                                      // EPI_OUT: colour (+ mu, sigma) heads
                     uint32_t v[16];
-                    tc::tmem_ld16(tmem_row + 128, v);
+                    tc::tmem_ld16(tmem_row, v);
                     tc::tmem_ld_wait();
-                    if (row_g < g.rows) g.out[row_g * g.C + 3] = __uint_as_float(v[0]) + bias_s[128];
+                    if (row_g < g.rows) {
+                        float* o = g.out + row_g * g.C;
+                        o[0] = __uint_as_float(v[0]) + bias_s[0];
+                        o[1] = __uint_as_float(v[1]) + bias_s[1];
+                        o[2] = __uint_as_float(v[2]) + bias_s[2];
+                        if (g.C == 6) {
+                            o[4] = __uint_as_float(v[3]) + bias_s[3];
+                            o[5] = __uint_as_float(v[4]) + bias_s[4];
+                        }
+                    }
                 }
-                if (g.mask && E.save_layer >= 0 && E.relu) {
-                    uint4* mp = reinterpret_cast<uint4*>(g.mask + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8);
-                    mp[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-                    mp[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
-                }
-            } else {                                             // EPI_OUT: colour (+ mu, sigma) heads
-                uint32_t v[16];
-                tc::tmem_ld16(tmem_row, v);
-                tc::tmem_ld_wait();
-                if (row_g < g.rows) {
-                    float* o = g.out + row_g * g.C;
-                    o[0] = __uint_as_float(v[0]) + bias_s[0];
-                    o[1] = __uint_as_float(v[1]) + bias_s[1];
-                    o[2] = __uint_as_float(v[2]) + bias_s[2];
-                    if (g.C == 6) {
-                        o[4] = __uint_as_float(v[3]) + bias_s[3];
-                        o[5] = __uint_as_float(v[4]) + bias_s[4];
+                tc::tc_fence_before_sync();          // TMEM reads done before the MMA warp may overwrite D
+                tc::fence_proxy_async_smem();        // act writes visible to tcgen05.mma / bulk store
+                if (T == 1) ctl->bias[(k + 1) & 1][tid] = nb;      // (the other buffer: nobody reads it now)
+                named_bar(1, kEpiThreads);
+                if (tid == 0) {
+                    tc::mbar_arrive(&ctl->act_ready[T]);
+                    if (g.save && E.save_layer >= 0) {
+                        tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
+                                     E.save_bytes);
+                        tc::bulk_commit();
+                        ++stores;
                     }
                 }
             }
-            tc::tc_fence_before_sync();          // TMEM reads done before the MMA warp may overwrite D
-            tc::fence_proxy_async_smem();        // act writes visible to tcgen05.mma / bulk store
-            named_bar(bar_id, 128);
-            if (row == 0) {
-                tc::mbar_arrive(&ctl->act_ready[T]);
-                if (g.save && E.save_layer >= 0) {
-                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
-                                 E.save_bytes);
-                    tc::bulk_commit();
-                    store_pending = true;
-                }
-            }
-            bias_s[2 * row] = nb.x;
-            bias_s[2 * row + 1] = nb.y;
-            named_bar(bar_id, 128);
         }
     }
-    if (row == 0) tc::bulk_wait_all<0>();
+    if (tid == 0) tc::bulk_wait_all<0>();
 }
 
-// ---- backward epilogue ------------------------------------------------------------------------
 __device__ __forceinline__ float masked(float x, uint32_t m, int bit) { return ((m >> bit) & 1u) ? x : 0.f; }
+
+__device__ __forceinline__ void bwd_chunk32(const uint32_t (&v)[32], uint32_t m, int c0, uint32_t act_u32, int row) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2)
+        pk[i / 2] = tc::pack_bf16(masked(__uint_as_float(v[i]), m, i), masked(__uint_as_float(v[i + 1]), m, i + 1));
+    store_chunk32(act_u32, row, c0, pk);
+}
 
 __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
     const Program& P = c_prog[1];
-    const int T = warp >> 2, q = warp & 3, row = q * 32 + lane;
-    const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
-    const uint32_t tmem_row = ctl->tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
-    const int bar_id = 1 + T;
+    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane, tid = warp * 32 + lane;
+    const uint32_t tmem_q = ctl->tmem_base + ((uint32_t)(q * 32) << 16);
     const int n_tiles = g.n_items * 2;
     const int n_epis = P.n_epis;
     uint32_t acc_phase = 0;
-    bool store_pending = false;
+    int stores = 0;
 
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-        const int tile_g = item * 2 + T;
-        const int64_t row_g = (int64_t)tile_g * 128 + row;
         for (int e = 0; e < n_epis; ++e) {
             const Epi E = P.epis[e];
-            uint32_t mk[8];
-            if (E.mask_layer >= 0) {
-                const uint4* mp = reinterpret_cast<const uint4*>(g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8);
-                const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-                mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
-                mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) mk[c] = 0xffffffffu;
-            }
-            if (E.mode != EPI_BWD_IN) {
-                tc::mbar_wait(&ctl->acc_full[T], acc_phase);
-                acc_phase ^= 1;
-                tc::tc_fence_after_sync();
-            }
-            if (row == 0 && store_pending) { tc::bulk_wait_read<0>(); store_pending = false; }
-            named_bar(bar_id, 128);
-            if (E.mode == EPI_BWD_IN) {
-                // dZ_dir = (g_rgb . W_rgb + g_musig . W_musig) * relu'(dir layer); column 128 = g_density
-                const float* w_rgb = g.bias + kHeadWRow * 256;          // aligned fp32 copies of the head weights
-                const float* w_musig = w_rgb + 3 * 256;
-                float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (row_g < g.rows) {
-                    const float* gp = g.gout + row_g * g.C;
-                    for (int c = 0; c < g.C; ++c) gr[c] = __ldg(gp + c);
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const int col = c * 32 + i;
-                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb + col));
-                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb + 256 + col));
-                        const float4 w2 = __ldg(reinterpret_cast<const float4*>(w_rgb + 512 + col));
-                        float x0 = gr[0] * w0.x + gr[1] * w1.x + gr[2] * w2.x;
-                        float x1 = gr[0] * w0.y + gr[1] * w1.y + gr[2] * w2.y;
-                        float x2 = gr[0] * w0.z + gr[1] * w1.z + gr[2] * w2.z;
-                        float x3 = gr[0] * w0.w + gr[1] * w1.w + gr[2] * w2.w;
-                        if (g.C == 6) {
-                            const float4 u0 = __ldg(reinterpret_cast<const float4*>(w_musig + col));
-                            const float4 u1 = __ldg(reinterpret_cast<const float4*>(w_musig + 256 + col));
-                            x0 += gr[4] * u0.x + gr[5] * u1.x;
-                            x1 += gr[4] * u0.y + gr[5] * u1.y;
-                            x2 += gr[4] * u0.z + gr[5] * u1.z;
-                            x3 += gr[4] * u0.w + gr[5] * u1.w;
-                        }
-                        pk[i / 2] = tc::pack_bf16(masked(x0, mk[c], i), masked(x1, mk[c], i + 1));
-                        pk[i / 2 + 1] = tc::pack_bf16(masked(x2, mk[c], i + 2), masked(x3, mk[c], i + 3));
+#pragma unroll 1
+            for (int T = 0; T < 2; ++T) {
+                const int tile_g = item * 2 + T;
+                const int64_t row_g = (int64_t)tile_g * 128 + row;
+                const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
+                const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
+                uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                if (E.mask_layer >= 0) {                 // this half's ReLU mask words (view branch: 2 words per half)
+                    const uint32_t* mp = g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8;
+                    if (E.mode == EPI_BWD_IN) {
+                        const uint2 m = __ldg(reinterpret_cast<const uint2*>(mp + 2 * hf));
+                        mk[0] = m.x; mk[1] = m.y;
+                    } else {
+                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(mp + 4 * hf));
+                        mk[0] = m.x; mk[1] = m.y; mk[2] = m.z; mk[3] = m.w;
                     }
-                    store_chunk32(act_u32, row, c * 32, pk);
                 }
-                const uint32_t b2 = act_u32 + 2u * 16384u + (uint32_t)row * 128u;
-                // columns 128..135 = [g_density, g_r, g_g, g_b, g_mu, g_sigma, 0, 0]: column 128 is the K extension of
-                // the next GEMM (weight rows 129..143 are zero); all six feed the head gradients in mlp_tc_dw.cu
-                st_shared_v4(b2 + (((0u ^ (uint32_t)row) & 7u) << 4), tc::pack_bf16(gr[3], gr[0]), tc::pack_bf16(gr[1], gr[2]),
-                             tc::pack_bf16(gr[4], gr[5]), 0u);
-                st_shared_v4(b2 + (((1u ^ (uint32_t)row) & 7u) << 4), 0u, 0u, 0u, 0u);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem_row + c * 32, v);
-                    tc::tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2)
-                        pk[i / 2] = tc::pack_bf16(masked(__uint_as_float(v[i]), mk[c], i), masked(__uint_as_float(v[i + 1]), mk[c], i + 1));
-                    store_chunk32(act_u32, row, c * 32, pk);
+                if (E.mode != EPI_BWD_IN) {
+                    tc::mbar_wait(&ctl->acc_full[T], (acc_phase >> T) & 1u);
+                    acc_phase ^= 1u << T;
+                    tc::tc_fence_after_sync();
                 }
-            }
-            tc::tc_fence_before_sync();
-            tc::fence_proxy_async_smem();
-            named_bar(bar_id, 128);
-            if (row == 0) {
-                if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
-                tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes, E.save_bytes);
-                tc::bulk_commit();
-                store_pending = true;
+                if (tid == 0 && stores >= 2) tc::bulk_wait_read<1>();
+                named_bar(1, kEpiThreads);
+                if (E.mode == EPI_BWD_IN) {
+                    // dZ_dir = (g_rgb . W_rgb + g_musig . W_musig) * relu'(dir layer); 64 of its 128 columns per half
+                    const float* w_rgb = g.bias + kHeadWRow * 256;          // aligned fp32 copies of the head weights
+                    const float* w_musig = w_rgb + 3 * 256;
+                    float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (row_g < g.rows) {
+                        const float* gp = g.gout + row_g * g.C;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c)
+                            if (c < g.C) gr[c] = __ldg(gp + c);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const int col = hf * 64 + c * 32 + i;
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb + col));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb + 256 + col));
+                            const float4 w2 = __ldg(reinterpret_cast<const float4*>(w_rgb + 512 + col));
+                            float x0 = gr[0] * w0.x + gr[1] * w1.x + gr[2] * w2.x;
+                            float x1 = gr[0] * w0.y + gr[1] * w1.y + gr[2] * w2.y;
+                            float x2 = gr[0] * w0.z + gr[1] * w1.z + gr[2] * w2.z;
+                            float x3 = gr[0] * w0.w + gr[1] * w1.w + gr[2] * w2.w;
+                            if (g.C == 6) {
+                                const float4 u0 = __ldg(reinterpret_cast<const float4*>(w_musig + col));
+                                const float4 u1 = __ldg(reinterpret_cast<const float4*>(w_musig + 256 + col));
+                                x0 += gr[4] * u0.x + gr[5] * u1.x;
+                                x1 += gr[4] * u0.y + gr[5] * u1.y;
+                                x2 += gr[4] * u0.z + gr[5] * u1.z;
+                                x3 += gr[4] * u0.w + gr[5] * u1.w;
+                            }
+                            pk[i / 2] = tc::pack_bf16(masked(x0, mk[c], i), masked(x1, mk[c], i + 1));
+                            pk[i / 2 + 1] = tc::pack_bf16(masked(x2, mk[c], i + 2), masked(x3, mk[c], i + 3));
+                        }
+                        store_chunk32(act_u32, row, hf * 64 + c * 32, pk);
+                    }
+                    if (hf == 0) {
+                        // columns 128..135 = [g_density, g_r, g_g, g_b, g_mu, g_sigma, 0, 0]: column 128 is the K extension
+                        // of the next GEMM (weight rows 129..143 are zero); all six feed the head gradients in mlp_tc_dw.cu
+                        const uint32_t b2 = act_u32 + 2u * 16384u + (uint32_t)row * 128u;
+                        st_shared_v4(b2 + (((0u ^ (uint32_t)row) & 7u) << 4), tc::pack_bf16(gr[3], gr[0]), tc::pack_bf16(gr[1], gr[2]),
+                                     tc::pack_bf16(gr[4], gr[5]), 0u);
+                        st_shared_v4(b2 + (((1u ^ (uint32_t)row) & 7u) << 4), 0u, 0u, 0u, 0u);
+                    }
+                } else {
+                    const int cb = hf * 128;
+                    uint32_t va[32], vb[32];
+                    tc::tmem_ld32(tmem_row + cb, va);
+#pragma unroll
+                    for (int c = 0; c < 4; c += 2) {                       // TMEM loads one chunk ahead of the math
+                        tc::tmem_ld_wait();
+                        tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
+                        bwd_chunk32(va, mk[c], cb + c * 32, act_u32, row);
+                        tc::tmem_ld_wait();
+                        if (c + 2 < 4) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
+                        bwd_chunk32(vb, mk[c + 1], cb + (c + 1) * 32, act_u32, row);
+                    }
+                }
+                tc::tc_fence_before_sync();
+                tc::fence_proxy_async_smem();
+                named_bar(1, kEpiThreads);
+                if (tid == 0) {
+                    if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
+                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes, E.save_bytes);
+                    tc::bulk_commit();
+                    ++stores;
+                }
             }
         }
     }
-    if (row == 0) tc::bulk_wait_all<0>();
+    if (tid == 0) tc::bulk_wait_all<0>();
 }
 
 template <int PI>
@@ -308,41 +339,91 @@ __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
     }
 }
 
+// ---- MMA issuer -------------------------------------------------------------------------------
 // The whole warp walks the op table (uniform control flow); one elected lane issues the MMAs and commits.
+struct Issuer {
+    uint32_t base16, tmem, full0, empty0, acc0, act0;
+    uint32_t ready_slot, ready_phase, act_phase;
+
+    __device__ __forceinline__ void wait_act(uint32_t tile) {
+        tc::mbar_wait_u32(act0 + tile * 8u, (act_phase >> tile) & 1u);
+        act_phase ^= 1u << tile;
+    }
+    __device__ __forceinline__ uint32_t wait_stage() {           // next ring stage in program order
+        const uint32_t s = ready_slot;
+        tc::mbar_wait_u32(full0 + s * 8u, ready_phase);
+        if (++ready_slot == kSlots) { ready_slot = 0; ready_phase ^= 1u; }
+        return s;
+    }
+};
+
+// One K = 256 layer part: for h in {0,1}: for tile in {0,1}: stages 4h..4h+3.  Tile 0 waits for the
+// stages, tile 1 releases them; every stage = two K = 16 MMAs.
+__device__ __forceinline__ void issue_h_part(Issuer& S, uint32_t idesc, bool commit_acc) {
+    uint32_t slot[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int T = 0; T < 2; ++T) {
+            if (h == 0) S.wait_act(T);
+            if (T == 0) {
+#pragma unroll
+                for (int c = 4 * h; c < 4 * h + 4; ++c) slot[c] = S.wait_stage();
+            }
+            tc::tc_fence_after_sync();
+            if (tc::elect_one()) {
+                const uint32_t d = S.tmem + (uint32_t)T * 256u;
+#pragma unroll
+                for (int c = 4 * h; c < 4 * h + 4; ++c) {
+                    const uint64_t a = ((uint64_t)kHi128 << 32) |
+                                       (uint64_t)(S.base16 + (uint32_t)T * (kActBytes >> 4) + (uint32_t)(c / 2) * 1024u + (uint32_t)(c % 2) * 4u);
+                    const uint64_t b = ((uint64_t)kHi64 << 32) | (uint64_t)(S.base16 + (kRingOff >> 4) + slot[c] * (kSlotBytes >> 4));
+                    tc::mma_f16_ss(d, a, b, idesc, c == 0 ? 0u : 1u);
+                    tc::mma_f16_ss(d, a + 2, b + 2, idesc, 1u);
+                    if (T == 1) tc::mma_commit_u32(S.empty0 + slot[c] * 8u);
+                }
+                if (h == 1 && commit_acc) tc::mma_commit_u32(S.acc0 + (uint32_t)T * 8u);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int PI>
 __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
     const Program& P = c_prog[PI];
-    const uint32_t base16 = smem_base >> 4;
-    const uint32_t tmem = ctl->tmem_base;
-    const uint32_t full0 = tc::smem_u32(&ctl->full[0]), empty0 = tc::smem_u32(&ctl->empty[0]);
-    const uint32_t acc0 = tc::smem_u32(&ctl->acc_full[0]), act0 = tc::smem_u32(&ctl->act_ready[0]);
+    Issuer S;
+    S.base16 = smem_base >> 4;
+    S.tmem = ctl->tmem_base;
+    S.full0 = tc::smem_u32(&ctl->full[0]);
+    S.empty0 = tc::smem_u32(&ctl->empty[0]);
+    S.acc0 = tc::smem_u32(&ctl->acc_full[0]);
+    S.act0 = tc::smem_u32(&ctl->act_ready[0]);
+    S.ready_slot = S.ready_phase = S.act_phase = 0;
     const int n_mmas = P.n_mmas;
-    uint32_t ready_slot = 0, ready_phase = 0, act_phase = 0;
     bool first_item = true;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         for (int i = 0; i < n_mmas; ++i) {
             const uint4 q0 = *reinterpret_cast<const uint4*>(&P.mmas[i]);
             const uint4 q1 = *(reinterpret_cast<const uint4*>(&P.mmas[i]) + 1);
             const uint32_t nk16 = (q1.y >> 16) & 0xFFu, flags = q1.y >> 24;
+            if (q1.w == OP_HPART) {
+                issue_h_part(S, q1.x, (flags & F_COMMIT_ACC) != 0);
+                continue;
+            }
             const uint32_t tile = q1.z & 0xFFu, n_wait = (q1.z >> 8) & 0xFFu, rel0 = (q1.z >> 16) & 0xFFu, rel1 = q1.z >> 24;
-            if ((flags & F_WAIT_ACT) || ((flags & F_WAIT_PREV) && !first_item)) {
-                tc::mbar_wait_u32(act0 + tile * 8u, (act_phase >> tile) & 1u);
-                act_phase ^= 1u << tile;
-            }
-            for (uint32_t w = 0; w < n_wait; ++w) {
-                tc::mbar_wait_u32(full0 + ready_slot * 8u, ready_phase);
-                if (++ready_slot == kSlots) { ready_slot = 0; ready_phase ^= 1u; }
-            }
+            if ((flags & F_WAIT_ACT) || ((flags & F_WAIT_PREV) && !first_item)) S.wait_act(tile);
+            for (uint32_t w = 0; w < n_wait; ++w) S.wait_stage();
             tc::tc_fence_after_sync();
             if (tc::elect_one()) {
-                const uint64_t a = ((uint64_t)q0.z << 32) | (uint64_t)(base16 + q0.x);
-                const uint64_t b = ((uint64_t)q0.w << 32) | (uint64_t)(base16 + q0.y);
-                const uint32_t d = tmem + (q1.y & 0xFFFFu);
+                const uint64_t a = ((uint64_t)q0.z << 32) | (uint64_t)(S.base16 + q0.x);
+                const uint64_t b = ((uint64_t)q0.w << 32) | (uint64_t)(S.base16 + q0.y);
+                const uint32_t d = S.tmem + (q1.y & 0xFFFFu);
                 if (nk16 > 0) tc::mma_f16_ss(d, a, b, q1.x, (flags & F_FIRST) ? 0u : 1u);
                 if (nk16 > 1) tc::mma_f16_ss(d, a + 2, b + 2, q1.x, 1u);
-                if (rel0 != 0xFFu) tc::mma_commit_u32(empty0 + rel0 * 8u);
-                if (rel1 != 0xFFu) tc::mma_commit_u32(empty0 + rel1 * 8u);
-                if (flags & F_COMMIT_ACC) tc::mma_commit_u32(acc0 + tile * 8u);
+                if (rel0 != 0xFFu) tc::mma_commit_u32(S.empty0 + rel0 * 8u);
+                if (rel1 != 0xFFu) tc::mma_commit_u32(S.empty0 + rel1 * 8u);
+                if (flags & F_COMMIT_ACC) tc::mma_commit_u32(S.acc0 + tile * 8u);
             }
             __syncwarp();
         }
@@ -485,8 +566,6 @@ __global__ void __launch_bounds__(256) encode_img_kernel(const float* __restrict
 }
 
 // ---- host: program construction ----------------------------------------------------------------
-constexpr uint32_t kHi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
-constexpr uint32_t kHi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) >> 32);
 
 struct RawMma {
     int tile, flags, nk16, n;            // n: MMA N (instruction descriptor)
@@ -495,6 +574,7 @@ struct RawMma {
     int b_seq;                           // ring stage holding B (-1: none, nk16 == 0)
     uint32_t b_off;
     int rel0, rel1;                      // ring stages released after this group
+    int kind = OP_GENERIC;               // OP_HPART: b_seq = first of 8 consecutive stages
 };
 
 struct Builder {
@@ -517,7 +597,19 @@ struct Builder {
     }
     void mma(int tile, int flags, int nk16, int n, int a_seq, uint32_t a_off, int b_seq, uint32_t b_off, int rel0 = -1,
              int rel1 = -1) {
-        ops.push_back(RawMma{tile, flags, nk16, n, a_seq, a_off, b_seq, b_off, rel0, rel1});
+        ops.push_back(RawMma{tile, flags, nk16, n, a_seq, a_off, b_seq, b_off, rel0, rel1, OP_GENERIC});
+    }
+    // the 16 MMA groups an OP_HPART entry stands for (issue_h_part executes exactly this order)
+    static void expand_h_part(const RawMma& hp, std::vector<RawMma>& out) {
+        for (int h = 0; h < 2; ++h)
+            for (int T = 0; T < 2; ++T)
+                for (int c = 4 * h; c < 4 * h + 4; ++c) {
+                    int flags = 0;
+                    if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
+                    if (c == 7 && (hp.flags & F_COMMIT_ACC)) flags |= F_COMMIT_ACC;
+                    out.push_back(RawMma{T, flags, 2, 256, -1, (c / 2) * 16384u + (c % 2) * 64u, hp.b_seq + c, 0,
+                                         T == 1 ? hp.b_seq + c : -1, -1, OP_GENERIC});
+                }
     }
     void epi(int mode, int relu, int save_layer, int mask_layer, int ncols, int bias_row, uint32_t save_bytes, int signal = 1) {
         P.epis[P.n_epis++] = Epi{(uint8_t)mode, (uint8_t)relu, (int8_t)save_layer, (int8_t)mask_layer, (uint16_t)ncols,
@@ -545,14 +637,7 @@ struct Builder {
     void h_part(uint16_t kind, int p, int k0, int n0, bool commit) {
         int w[8];
         for (int c = 0; c < 8; ++c) w[c] = load_w(16384, kind, p, 256, k0 + 32 * c, n0);
-        for (int h = 0; h < 2; ++h)
-            for (int T = 0; T < 2; ++T)
-                for (int c = 4 * h; c < 4 * h + 4; ++c) {
-                    int flags = 0;
-                    if (c == 0) flags |= F_FIRST | F_WAIT_ACT;
-                    if (c == 7 && commit) flags |= F_COMMIT_ACC;
-                    mma(T, flags, 2, 256, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
-                }
+        ops.push_back(RawMma{0, commit ? F_COMMIT_ACC : 0, 0, 256, -1, 0, w[0], 0, -1, -1, OP_HPART});
     }
     // pad the stage count to a multiple of the ring size (static slot indices), resolve the op table
     bool finish(char* why, size_t n) {
@@ -567,14 +652,32 @@ struct Builder {
         int ready = 0;
         bool released[kMaxLoads] = {};
         for (size_t i = 0; i < ops.size(); ++i) {
+            // schedule check on the expanded groups: every stage <= hi - kSlots must have been released by
+            // earlier groups, else the producer (which refills slots in order) and the issuer deadlock
+            std::vector<RawMma> sub;
+            if (ops[i].kind == OP_HPART) expand_h_part(ops[i], sub); else sub.push_back(ops[i]);
+            const int ready_before = ready;
+            for (const RawMma& o : sub) {
+                int hi = std::max(o.a_seq, o.b_seq);
+                if (o.rel1 > hi && o.nk16 == 0) hi = o.rel1;
+                for (int s = 0; s <= hi - kSlots; ++s)
+                    if (!released[s]) { snprintf(why, n, "mma group %zu needs stage %d but stage %d is still held", i, hi, s); return false; }
+                ready = std::max(ready, hi + 1);
+                if (o.rel0 >= 0) released[o.rel0] = true;
+                if (o.rel1 >= 0) released[o.rel1] = true;
+            }
             const RawMma& o = ops[i];
-            int hi = std::max(o.a_seq, o.b_seq);
-            if (o.rel1 > hi && o.nk16 == 0) hi = o.rel1;
-            // every stage <= hi - kSlots must have been released by earlier groups, else the producer
-            // (which refills slots in order) and the issuer deadlock
-            for (int s = 0; s <= hi - kSlots; ++s)
-                if (!released[s]) { snprintf(why, n, "mma group %zu needs stage %d but stage %d is still held", i, hi, s); return false; }
             Mma m{};
+            m.kind = (uint32_t)o.kind;
+            m.idesc = tc::idesc_bf16(128, o.n, 0, 0);
+            m.flags = (uint8_t)o.flags;
+            if (o.kind == OP_HPART) {
+                // the specialised routine takes its stages from the running ring position
+                if (ready_before != o.b_seq || ready != o.b_seq + 8) { snprintf(why, n, "h-part %zu does not start at the ring position", i); return false; }
+                P.mmas[P.n_mmas++] = m;
+                continue;
+            }
+            const int hi = ready - 1;
             const uint32_t a_byte = o.a_seq >= 0 ? kRingOff + (uint32_t)(o.a_seq % kSlots) * kSlotBytes + o.a_off
                                                  : (uint32_t)o.tile * kActBytes + o.a_off;
             const uint32_t b_byte = kRingOff + (uint32_t)((o.b_seq < 0 ? 0 : o.b_seq) % kSlots) * kSlotBytes + o.b_off;
@@ -582,17 +685,12 @@ struct Builder {
             m.b_lo = b_byte >> 4;
             m.a_hi = o.a_seq >= 0 ? kHi64 : kHi128;
             m.b_hi = kHi64;
-            m.idesc = tc::idesc_bf16(128, o.n, 0, 0);
             m.d_col = (uint16_t)(o.tile * 256);
             m.nk16 = (uint8_t)o.nk16;
-            m.flags = (uint8_t)o.flags;
             m.tile = (uint8_t)o.tile;
-            m.n_wait = (uint8_t)std::max(0, hi + 1 - ready);
-            ready = std::max(ready, hi + 1);
+            m.n_wait = (uint8_t)std::max(0, hi + 1 - ready_before);
             m.rel0 = o.rel0 >= 0 ? (uint8_t)(o.rel0 % kSlots) : 0xFF;
             m.rel1 = o.rel1 >= 0 ? (uint8_t)(o.rel1 % kSlots) : 0xFF;
-            if (o.rel0 >= 0) released[o.rel0] = true;
-            if (o.rel1 >= 0) released[o.rel1] = true;
             P.mmas[P.n_mmas++] = m;
         }
         if (ready != seq) { snprintf(why, n, "%d stages loaded but %d consumed", seq, ready); return false; }

@@ -42,8 +42,12 @@ struct __align__(16) Mma {
     uint16_t d_col;                   // TMEM column of the accumulator
     uint8_t nk16, flags;
     uint8_t tile, n_wait, rel0, rel1; // n_wait: ring stages to wait for first; rel*: slots released (0xFF none)
-    uint32_t pad;
+    uint32_t kind;                    // OP_GENERIC: the fields above; OP_HPART: a whole K = 256 layer part (below)
 };
+// OP_HPART: the regular bulk of both programs -- one K = 256 accumulation over the act buffer for both
+// tiles (8 consecutive ring stages, tiles interleaved half a layer apart), issued by a specialised
+// routine instead of 16 table entries.  Uses idesc and flags & F_COMMIT_ACC only.
+enum : uint32_t { OP_GENERIC = 0, OP_HPART = 1 };
 struct Epi {
     uint8_t mode, relu;
     int8_t save_layer;                // index into the activation / dZ save area, -1: none
