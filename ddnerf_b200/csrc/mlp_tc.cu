@@ -24,6 +24,7 @@
 // relu'_l down to layer 0, with transposed weight stages.  Every dZ tile image is stored for the
 // weight-gradient kernel (mlp_tc_dw.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -50,7 +51,11 @@ struct ChainArgs {
     uint32_t* mask;           // [layers][n_tiles][128][8]: fwd writes (or null), bwd reads
     int64_t rows;
     int n_items, C;
+    int save_alias;           // experiment knob (DDNERF_TC_SAVE_ALIAS): saves go to tile % save_alias (L2-resident)
+    unsigned long long* prof; // optional [grid][8] cycle counters (ddnerf_mlp_tc_set_profile_buffer), else null
 };
+
+__device__ __forceinline__ unsigned long long clk() { return clock64(); }
 
 // descriptor high words: K-major SWIZZLE_128B act buffer (SBO = 8 rows x 128 B), SWIZZLE_64B ring stages
 constexpr uint32_t kHi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
@@ -84,26 +89,34 @@ __device__ __forceinline__ void store_chunk32(uint32_t act_u32, int row, int c0,
 constexpr int kEpiThreads = 256;
 
 // 32 accumulator columns [c0, c0+32) of this thread's row: + bias, optional ReLU, -> bf16, stored as
-// four 16-byte chunks of the act buffer.  Returns the sign bitmask (bit i = value i > 0).
-__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const float* __restrict__ bias_s, int c0, bool relu,
+// four 16-byte chunks of the act buffer.  Returns the ReLU mask (bit i set: value i has its sign bit
+// clear, i.e. is positive -- or +0, where passing the gradient is immaterial), collected with one
+// funnel shift per value.
+template <bool RELU>
+__device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const float* __restrict__ bias_s, int c0,
                                                 uint32_t act_u32, int row) {
     uint32_t pk[16];
-    uint32_t m = 0;
+    uint32_t neg = 0;
+    float x[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
         const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-        float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
-        float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
-        m |= (x0 > 0.f ? 1u : 0u) << i;
-        m |= (x1 > 0.f ? 1u : 0u) << (i + 1);
-        m |= (x2 > 0.f ? 1u : 0u) << (i + 2);
-        m |= (x3 > 0.f ? 1u : 0u) << (i + 3);
-        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-        pk[i / 2] = tc::pack_bf16(x0, x1);
-        pk[i / 2 + 1] = tc::pack_bf16(x2, x3);
+        x[i] = __uint_as_float(v[i]) + b.x;
+        x[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+        x[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+        x[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+    }
+    if (RELU) {
+#pragma unroll
+        for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(x[i]), neg, 1);     // bit i = sign of x[i]
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const float a = RELU ? fmaxf(x[i], 0.f) : x[i], c = RELU ? fmaxf(x[i + 1], 0.f) : x[i + 1];
+        pk[i / 2] = tc::pack_bf16(a, c);
     }
     store_chunk32(act_u32, row, c0, pk);
-    return m;
+    return ~neg;
 }
 
 __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
@@ -115,6 +128,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
     uint32_t acc_phase = 0;                  // bit T: parity of acc_full[T]
     int stores = 0;                          // bulk stores issued by thread 0
     uint32_t k = 0;                          // running epilogue count: parity selects the bias buffer
+    unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
     ctl->bias[0][tid] = __ldg(g.bias + P.epis[0].bias_off + tid);          // bias of the first epilogue
     named_bar(1, kEpiThreads);
@@ -129,27 +143,42 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                 const int64_t row_g = (int64_t)tile_g * 128 + row;
                 const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
                 const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
+                const unsigned long long tw0 = g.prof ? clk() : 0;
                 tc::mbar_wait(&ctl->acc_full[T], (acc_phase >> T) & 1u);
                 acc_phase ^= 1u << T;
                 tc::tc_fence_after_sync();
+                const unsigned long long tw1 = g.prof ? clk() : 0;
                 if (g.save) {            // this tile's previous bulk store must have finished reading the act buffer
                     if (tid == 0 && stores >= 2) tc::bulk_wait_read<1>();
                     named_bar(1, kEpiThreads);
                 }
+                const unsigned long long tw2 = g.prof ? clk() : 0;
                 if (E.mode == EPI_ACT || E.mode == EPI_DIR) {
                     const int nc = (E.mode == EPI_DIR) ? 64 : 128;         // columns of this half
                     const int cb = hf * nc;
                     uint32_t mk[4] = {0u, 0u, 0u, 0u};
                     uint32_t va[32], vb[32];
                     tc::tmem_ld32(tmem_row + cb, va);
+                    if (E.relu) {
 #pragma unroll
-                    for (int c = 0; c < 4; c += 2) {                       // TMEM loads one chunk ahead of the math
-                        tc::tmem_ld_wait();
-                        if ((c + 1) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
-                        if (c * 32 < nc) mk[c] = epi_chunk32(va, bias_s, cb + c * 32, E.relu != 0, act_u32, row);
-                        tc::tmem_ld_wait();
-                        if ((c + 2) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
-                        if ((c + 1) * 32 < nc) mk[c + 1] = epi_chunk32(vb, bias_s, cb + (c + 1) * 32, E.relu != 0, act_u32, row);
+                        for (int c = 0; c < 4; c += 2) {                   // TMEM loads one chunk ahead of the math
+                            tc::tmem_ld_wait();
+                            if ((c + 1) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
+                            if (c * 32 < nc) mk[c] = epi_chunk32<true>(va, bias_s, cb + c * 32, act_u32, row);
+                            tc::tmem_ld_wait();
+                            if ((c + 2) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
+                            if ((c + 1) * 32 < nc) mk[c + 1] = epi_chunk32<true>(vb, bias_s, cb + (c + 1) * 32, act_u32, row);
+                        }
+                    } else {                                               // fc_feat: no activation, no mask
+#pragma unroll
+                        for (int c = 0; c < 4; c += 2) {
+                            tc::tmem_ld_wait();
+                            tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
+                            epi_chunk32<false>(va, bias_s, cb + c * 32, act_u32, row);
+                            tc::tmem_ld_wait();
+                            if (c + 2 < 4) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
+                            epi_chunk32<false>(vb, bias_s, cb + (c + 1) * 32, act_u32, row);
+                        }
                     }
                     if (E.mode == EPI_DIR && hf == 0) {                    // column 128 = density (fc_alpha)
                         uint32_t v[16];
@@ -181,14 +210,17 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                         }
                     }
                 }
+                const unsigned long long tw3 = g.prof ? clk() : 0;
                 tc::tc_fence_before_sync();          // TMEM reads done before the MMA warp may overwrite D
                 tc::fence_proxy_async_smem();        // act writes visible to tcgen05.mma / bulk store
                 if (T == 1) ctl->bias[(k + 1) & 1][tid] = nb;      // (the other buffer: nobody reads it now)
                 named_bar(1, kEpiThreads);
                 if (tid == 0) {
                     tc::mbar_arrive(&ctl->act_ready[T]);
+                    if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     if (g.save && E.save_layer >= 0) {
-                        tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes,
+                        const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
+                        tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
                                      E.save_bytes);
                         tc::bulk_commit();
                         ++stores;
@@ -198,6 +230,11 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
         }
     }
     if (tid == 0) tc::bulk_wait_all<0>();
+    if (g.prof && tid == 0) {
+        unsigned long long* o = g.prof + (size_t)blockIdx.x * 8;
+        o[3] = t_wait; o[4] = t_busy; o[5] = n_epi;     // epilogues: waiting for MMAs / busy / count
+        o[6] = t_pre; o[7] = t_work;                    // of busy: store-drain + barrier / accumulator -> act buffer
+    }
 }
 
 __device__ __forceinline__ float masked(float x, uint32_t m, int bit) { return ((m >> bit) & 1u) ? x : 0.f; }
@@ -218,6 +255,7 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
     const int n_epis = P.n_epis;
     uint32_t acc_phase = 0;
     int stores = 0;
+    unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         for (int e = 0; e < n_epis; ++e) {
@@ -228,6 +266,7 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                 const int64_t row_g = (int64_t)tile_g * 128 + row;
                 const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
                 const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
+                const unsigned long long tw0 = g.prof ? clk() : 0;
                 uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
                 if (E.mask_layer >= 0) {                 // this half's ReLU mask words (view branch: 2 words per half)
                     const uint32_t* mp = g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8;
@@ -244,8 +283,10 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                     acc_phase ^= 1u << T;
                     tc::tc_fence_after_sync();
                 }
+                const unsigned long long tw1 = g.prof ? clk() : 0;
                 if (tid == 0 && stores >= 2) tc::bulk_wait_read<1>();
                 named_bar(1, kEpiThreads);
+                const unsigned long long tw2 = g.prof ? clk() : 0;
                 if (E.mode == EPI_BWD_IN) {
                     // dZ_dir = (g_rgb . W_rgb + g_musig . W_musig) * relu'(dir layer); 64 of its 128 columns per half
                     const float* w_rgb = g.bias + kHeadWRow * 256;          // aligned fp32 copies of the head weights
@@ -305,12 +346,15 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                         bwd_chunk32(vb, mk[c + 1], cb + (c + 1) * 32, act_u32, row);
                     }
                 }
+                const unsigned long long tw3 = g.prof ? clk() : 0;
                 tc::tc_fence_before_sync();
                 tc::fence_proxy_async_smem();
                 named_bar(1, kEpiThreads);
                 if (tid == 0) {
                     if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
-                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_g) * kActBytes, act_all + T * kActBytes, E.save_bytes);
+                    if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
+                    const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
+                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes, E.save_bytes);
                     tc::bulk_commit();
                     ++stores;
                 }
@@ -318,6 +362,11 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
         }
     }
     if (tid == 0) tc::bulk_wait_all<0>();
+    if (g.prof && tid == 0) {
+        unsigned long long* o = g.prof + (size_t)blockIdx.x * 8;
+        o[3] = t_wait; o[4] = t_busy; o[5] = n_epi;
+        o[6] = t_pre; o[7] = t_work;
+    }
 }
 
 template <int PI>
@@ -344,14 +393,20 @@ __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
 struct Issuer {
     uint32_t base16, tmem, full0, empty0, acc0, act0;
     uint32_t ready_slot, ready_phase, act_phase;
+    unsigned long long t_act, t_stage;      // cycles spent waiting (profiling)
+    bool prof;
 
     __device__ __forceinline__ void wait_act(uint32_t tile) {
+        const unsigned long long t0 = prof ? clk() : 0;
         tc::mbar_wait_u32(act0 + tile * 8u, (act_phase >> tile) & 1u);
         act_phase ^= 1u << tile;
+        if (prof) t_act += clk() - t0;
     }
     __device__ __forceinline__ uint32_t wait_stage() {           // next ring stage in program order
         const uint32_t s = ready_slot;
+        const unsigned long long t0 = prof ? clk() : 0;
         tc::mbar_wait_u32(full0 + s * 8u, ready_phase);
+        if (prof) t_stage += clk() - t0;
         if (++ready_slot == kSlots) { ready_slot = 0; ready_phase ^= 1u; }
         return s;
     }
@@ -400,6 +455,9 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
     S.acc0 = tc::smem_u32(&ctl->acc_full[0]);
     S.act0 = tc::smem_u32(&ctl->act_ready[0]);
     S.ready_slot = S.ready_phase = S.act_phase = 0;
+    S.t_act = S.t_stage = 0;
+    S.prof = g.prof != nullptr;
+    const unsigned long long t_begin = clk();
     const int n_mmas = P.n_mmas;
     bool first_item = true;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -428,6 +486,12 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
             __syncwarp();
         }
         first_item = false;
+    }
+    if (S.prof && (threadIdx.x & 31) == 0) {
+        unsigned long long* o = g.prof + (size_t)blockIdx.x * 8;
+        o[0] = clk() - t_begin;     // issuer: total
+        o[1] = S.t_act;             // issuer: waiting for epilogues (act_ready)
+        o[2] = S.t_stage;           // issuer: waiting for ring stages (weights / encoded blocks)
     }
 }
 
@@ -523,46 +587,90 @@ __global__ void __launch_bounds__(256) pack_bias_kernel(const PackArgs a) {
 }
 
 // ---- encoder writing bf16 operand images -------------------------------------------------------
-// One thread per (sample row, degree l): the 96 IPE features of a row go to three [128 x 32]
-// SWIZZLE_64B blocks of the item image, the 27 (+5 zero) view-direction features to its dir block.
-__global__ void __launch_bounds__(256) encode_img_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
+// One thread per sample row: cone -> Gaussian, the 96 IPE features (three [128 x 32] SWIZZLE_64B blocks
+// of the item image) and the 27 (+5 zero) view-direction features, stored as 16-byte chunks.  The
+// values are rounded to bf16 (2^-9 relative), so the transcendental functions use the SFU: the argument
+// follows the reference's fp32 steps (y = x 2^l, the floored remainder by fl32(100 pi) of safe_sin, the
+// fp32 sum y + fl32(pi/2) of the cosine half, math_utils.py:128-166), then a two-term Cody-Waite
+// reduction to [-pi, pi] and sin.approx (absolute error ~1e-6).
+__device__ __forceinline__ float sfu_sin(float x) {                // |x| <= 100 pi
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555e-7f, r);
+    return __sinf(r);
+}
+__device__ __forceinline__ float safe_arg_fast(float x) {          // math_utils.py:154-166
+    const float T = 314.15927124f;
+    if (fabsf(x) < T) return x;
+    const float q = floorf(x * (1.0f / T));
+    return fmaf(-q, T, x);
+}
+
+__global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
                                                          uint8_t* __restrict__ img, int64_t N, int S, int ray_shape,
                                                          int64_t rows_padded) {
-    const int l = threadIdx.x & 15;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_padded) return;
     const int64_t item = row / kItemRows;
     const int T = (int)(row % kItemRows) / 128, r = (int)(row % 128);
     uint8_t* ib = img + item * kEncItemBytes;
-    float sn[3] = {0.f, 0.f, 0.f}, cs[3] = {0.f, 0.f, 0.f}, d3[3] = {0.f, 0.f, 0.f};
-    const bool valid = row < N * S;
-    if (valid) {
+    uint32_t w[48];                       // 96 bf16: feature f = h*48 + l*3 + a in word f/2
+    uint32_t dw[16];                      // 32 bf16 of the direction block
+#pragma unroll
+    for (int i = 0; i < 48; ++i) w[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dw[i] = 0u;
+    if (row < N * S) {
         const int64_t ray = row / S;
         const int i = (int)(row - ray * S);
         const RayGeom g = load_ray(rays, ray);
         const float* tp = t_vals + ray * (S + 1) + i;
         const Gauss3 s = cast_interval(g, __ldg(tp), __ldg(tp + 1), ray_shape);
-        ipe_degree(s, l, sn, cs);
-        if (l < 9) dir_group(g, l, d3);
-    }
+        const float m[3] = {s.mx, s.my, s.mz}, c[3] = {s.cx, s.cy, s.cz};
+        float f[96];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+        for (int l = 0; l < 16; ++l) {
+            const float scale = (float)(1 << l), sc2 = scale * scale;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int f = h * 48 + l * 3 + a;
-            const int b = f >> 5, kk = f & 31;
-            const uint32_t blk = b < 2 ? (uint32_t)T * 16384u + (uint32_t)b * 8192u : 32768u + (uint32_t)T * 8192u;
-            *reinterpret_cast<__nv_bfloat16*>(ib + blk + tc::sw64_off(r, kk)) = __float2bfloat16_rn(h ? cs[a] : sn[a]);
+            for (int a = 0; a < 3; ++a) {
+                const float y = m[a] * scale;
+                const float e = __expf(-0.5f * (c[a] * sc2));
+                f[l * 3 + a] = e * sfu_sin(safe_arg_fast(y));
+                f[48 + l * 3 + a] = e * sfu_sin(safe_arg_fast(y + 1.57079637f));
+            }
         }
-    }
-    const uint32_t dblk = 49152u + (uint32_t)T * 8192u;
-    if (l < 9) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-            *reinterpret_cast<__nv_bfloat16*>(ib + dblk + tc::sw64_off(r, l * 3 + a)) = __float2bfloat16_rn(d3[a]);
-    } else if (l < 14) {
-        *reinterpret_cast<__nv_bfloat16*>(ib + dblk + tc::sw64_off(r, 27 + (l - 9))) = __float2bfloat16_rn(0.f);
+        for (int i = 0; i < 48; ++i) w[i] = tc::pack_bf16(f[2 * i], f[2 * i + 1]);
+        float d[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = 0.f;
+        const float v[3] = {g.vx, g.vy, g.vz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {                    // [v | sin v, cos v | sin 2v, cos 2v | sin 4v, cos 4v | sin 8v, cos 8v]
+            d[a] = v[a];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float x = v[a] * (float)(1 << k);  // |x| <= 8
+                d[3 + 6 * k + a] = __sinf(x);
+                d[6 + 6 * k + a] = __cosf(x);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dw[i] = tc::pack_bf16(d[2 * i], d[2 * i + 1]);
     }
+    const uint32_t sw = ((uint32_t)r >> 1) & 3u;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {                        // xyz block b = features 32 b .. 32 b + 31
+        uint8_t* bp = ib + (b < 2 ? (uint32_t)T * 16384u + (uint32_t)b * 8192u : 32768u + (uint32_t)T * 8192u) + (uint32_t)r * 64u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(bp + (((uint32_t)j ^ sw) << 4)) =
+                make_uint4(w[16 * b + 4 * j], w[16 * b + 4 * j + 1], w[16 * b + 4 * j + 2], w[16 * b + 4 * j + 3]);
+    }
+    uint8_t* dp = ib + 49152u + (uint32_t)T * 8192u + (uint32_t)r * 64u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dp + (((uint32_t)j ^ sw) << 4)) = make_uint4(dw[4 * j], dw[4 * j + 1], dw[4 * j + 2], dw[4 * j + 3]);
 }
 
 // ---- host: program construction ----------------------------------------------------------------
@@ -803,6 +911,8 @@ int ensure_programs() {
     return g_upload_rc;
 }
 
+unsigned long long* g_prof_buffer = nullptr;      // diagnostic hook, see ddnerf_mlp_tc_set_profile_buffer
+
 int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -822,6 +932,13 @@ using namespace ddnerf;
         DDNERF_CHECK_ARG(rc__ == 0, "%s: device setup failed (%d): %s", who, rc__, cudaGetErrorString(cudaGetLastError())); \
     } while (0)
 
+/* Diagnostic hook: when set to a device buffer of >= 8 * n_SMs uint64, the chain kernels write per-CTA cycle
+ * counters [issuer total, issuer waiting on epilogues, issuer waiting on ring stages, epilogues waiting on
+ * MMAs, epilogues busy, epilogue count, -, -]; NULL (default) switches the instrumentation off. */
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_set_profile_buffer(void* dev_u64) {
+    g_prof_buffer = static_cast<unsigned long long*>(dev_u64);
+    return 0;
+}
 /* 0 when the static kernel programs (ring schedule, op tables) are consistent; host-only check */
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_program_check(void) {
     Programs* S = build_programs();
@@ -862,7 +979,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_encode(const float* rays, const float
     DDNERF_CHECK_ARG(ray_shape == 0 || ray_shape == 1, "mlp_tc_encode: ray_shape=%d (0 cone, 1 cylinder)", ray_shape);
     if (N * S == 0) return 0;
     const int64_t rows_padded = ddnerf_mlp_tc_items(N * S) * tcmlp::kItemRows;
-    encode_img_kernel<<<ceil_div(rows_padded, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    encode_img_kernel<<<ceil_div(rows_padded, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         rays, t_vals, static_cast<uint8_t*>(enc_img), N, S, ray_shape, rows_padded);
     DDNERF_LAUNCHED("mlp_tc_encode", 1);
     return 0;
@@ -888,6 +1005,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float
     g.rows = rows;
     g.n_items = (int)n_items;
     g.C = out_channels;
+    if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
+    g.prof = g_prof_buffer;
     const int grid = (int)std::min<int64_t>(n_items, sm_count());
     mlp_tc_chain_kernel<0><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED("mlp_tc_forward", 1);
@@ -913,6 +1032,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const f
     g.rows = rows;
     g.n_items = (int)n_items;
     g.C = out_channels;
+    if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
+    g.prof = g_prof_buffer;
     const int grid = (int)std::min<int64_t>(n_items, sm_count());
     mlp_tc_chain_kernel<1><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED("mlp_tc_backward_dx", 1);

@@ -137,6 +137,10 @@ int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const v
  * (0 = consistent) and the (layer-op, tile range) split of backward_dw over `sms` SMs, written as
  * (op, first tile, end tile) uint32 triples; returns the number of work items. */
 int ddnerf_mlp_tc_program_check(void);
+/* Diagnostic hook: a device buffer of >= 8 * n_SMs uint64 into which the chain kernels write per-CTA cycle
+ * counters (issuer total / waiting on epilogues / waiting on ring stages, epilogues waiting on MMAs / busy /
+ * count); NULL (default) switches the instrumentation off. */
+int ddnerf_mlp_tc_set_profile_buffer(void* dev_u64);
 int ddnerf_mlp_tc_dw_plan(int64_t rows, int sms, uint32_t* triples, int max_items);
 
 /* Descriptor self-test of the tcgen05 path (test infrastructure of the bf16 MLP): one CTA computes

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--samples", type=int, default=128)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--save", action="store_true", help="training forward (store activations + masks)")
+    ap.add_argument("--prof", action="store_true", help="print the chain kernels' per-role cycle counters")
     args = ap.parse_args()
     from oracle import ddnerf_oracle as orc
     from ddnerf_b200 import _lib, mlp_tc
@@ -102,6 +103,20 @@ def main():
         tot = res["fwd_ms"] + res["dx_ms"] + res["dw_ms"]
         res["train_tflops"] = 2.0 * (610304 * 2 + 557696) * rows / tot / 1e9
     print(json.dumps(res))
+    if args.prof:
+        buf = torch.zeros(148 * 8, device="cuda", dtype=torch.int64)
+        lib.ddnerf_mlp_tc_set_profile_buffer(_p(buf))
+        runs = [("fwd", fwd)] + ([("dx", dx)] if args.save else [])
+        for name, fn in runs:
+            buf.zero_()
+            fn()
+            torch.cuda.synchronize()
+            b = buf.view(148, 8).double()
+            tot, t_act, t_stage, e_wait, e_busy, n, e_pre, e_work = [b[:, i].mean().item() for i in range(8)]
+            print(f"{name}: issuer total {tot:.0f} cyc | waits: epilogue {100 * t_act / tot:.1f}% ring {100 * t_stage / tot:.1f}% | "
+                  f"epilogue busy {e_busy / max(n, 1):.0f} cyc each (store drain + barrier {e_pre / max(n, 1):.0f}, accumulator -> act buffer "
+                  f"{e_work / max(n, 1):.0f}), waiting on MMA {e_wait / max(n, 1):.0f} cyc each, n={n:.0f}")
+        lib.ddnerf_mlp_tc_set_profile_buffer(None)
 
 
 if __name__ == "__main__":
