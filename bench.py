@@ -151,6 +151,80 @@ def run_reference(args, cfg, kind, desc):
     print(json.dumps(line), flush=True)
 
 
+def run_render(args, dev, world, rank, dist):
+    """Full-frame render of BASELINE.json configs[2]: config_ff.yml DDNeRF, 1008x756 forward-facing NDC rays,
+    16+16 samples, validation mode exactly as render_video.py:36-48,73-78 sets it up (pdf_padding off,
+    gaussian_smooth_factor = final_smooth, det sampling, noise std 1.0), pixel rows split across ranks, no
+    collective.  Returns the dict that goes under "render" in the JSON line."""
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import full_frame_rays
+    from ddnerf_b200.trainer import shard_rows
+    cfg, kind = preset("config_ff")
+    cfg.train_params.pdf_padding = False
+    cfg.train_params.gaussian_smooth_factor = cfg.train_params.final_smooth
+    ro, rd, rad, near, far = full_frame_rays(kind)
+    H, W = ro.shape[:2]
+    lo, hi = shard_rows(H, rank, world)
+    cfg.nerf.validation.chunksize = args.render_chunk if args.render_chunk > 0 else (hi - lo) * W
+    host = tuple(t[lo:hi].contiguous().pin_memory() for t in (ro, rd, rad))
+    torch.manual_seed(cfg.experiment.randomseed)
+    model = M.DDNerfModel(cfg)
+    model.to(dev)
+    model.eval()
+    model.record_distributions = False
+    for net in (model.coarse, model.fine):
+        net.mlp_mode = args.mlp_mode
+    resident = tuple(t.to(dev) for t in host)
+    img_host = torch.empty((hi - lo), W, 4, pin_memory=True)
+    stage = [torch.empty_like(t, device=dev) for t in host]
+
+    def frame_resident():
+        with torch.no_grad():
+            return model.run_iter(*resident, mode="validation")
+
+    def frame_e2e():
+        for dst, src in zip(stage, host):
+            dst.copy_(src, non_blocking=True)
+        with torch.no_grad():
+            out = model.run_iter(*stage, mode="validation")
+        img_host[..., :3].copy_(out[1]["rgb"], non_blocking=True)
+        img_host[..., 3].copy_(out[1]["disp"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, count):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(count):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    frames = args.render_frames
+    for _ in range(3):
+        frame_resident()
+    ms = timed(frame_resident, frames)
+    frame_e2e()
+    ms_e2e = timed(frame_e2e, frames)
+    rays = H * W
+    return {"metric": "render_rays_per_sec", "value": rays * frames / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_frame": ms / frames, "scaling": "strong",
+            "e2e": {"value": rays * frames / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_frame": ms_e2e / frames,
+                    "h2d_bytes_per_frame": sum(t.numel() * 4 for t in host) * world,
+                    "d2h_bytes_per_frame": img_host.numel() * 4 * world},
+            "workload": "config_ff.yml DDNeRF 1008x756 full frame, 16+16 samples, validation mode, rows split over ranks",
+            "frames": frames, "chunk_rays": int(cfg.nerf.validation.chunksize)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +235,9 @@ def main():
     ap.add_argument("--mlp-mode", default=os.environ.get("DDNERF_MLP_MODE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the full-frame render leg (configs[2])")
+    ap.add_argument("--render-frames", type=int, default=5)
+    ap.add_argument("--render-chunk", type=int, default=0, help="rays per chunk of the render leg (0: one chunk per rank)")
     args = ap.parse_args()
 
     from ddnerf_b200.config import preset
@@ -180,6 +257,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout; stdout carries one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     os.environ["DDNERF_MLP_MODE"] = args.mlp_mode
@@ -275,6 +354,8 @@ def main():
                      "peak_kind": f"{pk_kind} bf16 sustained (MEASURED_PEAKS.json)",
                      "mlp_ms_per_step": mlp_ms / K if K else None},
     }
+    if not args.no_render:
+        line["render"] = run_render(args, dev, world, rank, dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = min(args.cpu_rays, n_rays)
         rps, sec, threads = cpu_baseline(cfg, kind, n_cpu, 2, 1)
