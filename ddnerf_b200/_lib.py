@@ -52,6 +52,7 @@ SIGNATURES = {
     "ddnerf_mlp_tc_dw_plan": (c_i, [c_l, c_i, ctypes.POINTER(ctypes.c_uint32), c_i]),
     "ddnerf_tc_gemm_selftest": (c_i, [c_p, c_l, c_p, c_l, c_p, c_i, c_i, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                       ctypes.POINTER(ctypes.c_uint32), c_p]),
+    "ddnerf_tc_mma_rate": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p]),
     "ddnerf_composite_forward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 7 + [c_l, c_i, c_p]),
     "ddnerf_composite_backward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 8 + [c_l, c_i, c_p]),
     "ddnerf_dp_loss_forward": (c_i, [c_p] * 8 + [c_i, c_p, c_p, c_l, c_i, c_i, c_p]),

@@ -87,3 +87,75 @@ extern "C" DDNERF_EXPORT int ddnerf_tc_gemm_selftest(const void* a_img, int64_t 
     DDNERF_LAUNCHED("tc_gemm_selftest", 1);
     return 0;
 }
+
+// ---- tensor-pipe rate probe (diagnostic): back-to-back tcgen05.mma on resident, arbitrary operands ----------
+namespace ddnerf {
+namespace {
+
+struct RateArgs {
+    int n_mma, commit_every, pair, N;
+    unsigned long long* cycles;      // [gridDim.x]
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tc_rate_kernel(RateArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];      // [A 64 KB | B 32 KB], contents irrelevant (finite garbage)
+    __shared__ uint64_t bar_done, bar_stage, bar_stage2;
+    __shared__ uint32_t tmem_holder;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = tc::cluster_ctarank();
+    for (int i = threadIdx.x; i < (96 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar_done, 1);
+        tc::mbar_init(&bar_stage, 1);
+        tc::mbar_init(&bar_stage2, 1);
+        tc::fence_barrier_init();
+    }
+    tc::fence_proxy_async_smem();
+    tc::cluster_sync();
+    if (warp == 0) { if (g.pair) tc::tmem_alloc2(&tmem_holder, 512); else tc::tmem_alloc(&tmem_holder, 512); }
+    tc::tc_fence_before_sync();
+    tc::cluster_sync();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_holder;
+    if (threadIdx.x == 0 && (!g.pair || rank == 0)) {
+        const uint32_t base16 = tc::smem_u32(smem) >> 4;
+        constexpr uint32_t hi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
+        constexpr uint32_t hi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) >> 32);
+        const uint32_t idesc = tc::idesc_bf16(g.pair ? 256 : 128, g.N, 0, 0);
+        const int ce = g.commit_every < 0 ? -g.commit_every : g.commit_every;       // negative: two commits at a time
+        int left = ce;
+        const unsigned long long t0 = clock64();
+        for (int i = 0; i < g.n_mma; ++i) {
+            const uint64_t a = ((uint64_t)hi128 << 32) | (uint64_t)(base16 + (uint32_t)((i & 7) / 2) * 1024u + (uint32_t)(i & 1) * 2u);
+            const uint64_t b = ((uint64_t)hi64 << 32) | (uint64_t)(base16 + 4096u + (uint32_t)((i >> 1) & 1) * 512u + (uint32_t)(i & 1) * 2u);
+            const uint32_t d = tmem + (uint32_t)((i >> 4) & 1) * 256u;
+            if (g.pair) tc::mma2_f16_ss(d, a, b, idesc, 1u); else tc::mma_f16_ss(d, a, b, idesc, 1u);
+            if (ce > 0 && --left == 0) {
+                left = ce;
+                if (g.pair) tc::mma2_commit_u32(tc::smem_u32(&bar_stage)); else tc::mma_commit(&bar_stage);
+                if (g.commit_every < 0) { if (g.pair) tc::mma2_commit_u32(tc::smem_u32(&bar_stage2)); else tc::mma_commit(&bar_stage2); }
+            }
+        }
+        if (g.pair) tc::mma2_commit_u32(tc::smem_u32(&bar_done)); else tc::mma_commit(&bar_done);
+        tc::mbar_wait(&bar_done, 0);
+        g.cycles[blockIdx.x] = clock64() - t0;
+    }
+    tc::tc_fence_before_sync();
+    tc::cluster_sync();
+    if (warp == 0) { if (g.pair) tc::tmem_dealloc2(tmem, 512); else tc::tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace
+}  // namespace ddnerf
+
+/* Diagnostic: cycles one CTA (pair = 0) or a CTA pair (pair = 1, cta_group::2) needs to run n_mma back-to-back
+ * M = 128 (256) x N x 16 bf16 MMAs on resident operands, committing to an mbarrier every `commit_every` MMAs
+ * (0 = never).  cycles_out: one uint64 per CTA of a 148-CTA launch (leader CTAs only in pair mode). */
+extern "C" DDNERF_EXPORT int ddnerf_tc_mma_rate(int pair, int N, int n_mma, int commit_every, void* cycles_out, void* stream) {
+    DDNERF_CHECK_ARG(cycles_out && n_mma > 0 && N >= 16 && N <= 256 && N % 16 == 0, "tc_mma_rate: bad arguments");
+    RateArgs g{n_mma, commit_every, pair, N, static_cast<unsigned long long*>(cycles_out)};
+    cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 97 * 1024);
+    tc_rate_kernel<<<148, 128, 97 * 1024, static_cast<cudaStream_t>(stream)>>>(g);
+    DDNERF_LAUNCHED("tc_mma_rate", 1);
+    return 0;
+}

@@ -152,6 +152,11 @@ int ddnerf_tc_gemm_selftest(const void* a_img, int64_t a_bytes, const void* b_im
                             float* d_out, int N, int nk16, uint64_t a_desc, uint64_t b_desc,
                             uint32_t idesc, const uint32_t* stepping, void* stream);
 
+/* Diagnostic: cycles one CTA (pair = 0) or a CTA pair (pair = 1, tcgen05 cta_group::2) needs for n_mma
+ * back-to-back M = 128 (256) x N x 16 bf16 MMAs on resident operands, committing to an mbarrier every
+ * `commit_every` MMAs (0 = never).  cycles_out: one uint64 per CTA of a 148-CTA launch. */
+int ddnerf_tc_mma_rate(int pair, int N, int n_mma, int commit_every, void* cycles_out, void* stream);
+
 /* ---- K4: alpha compositing (general_utils/volume_rendering_utils.py:6-84) ---------------- */
 /* raw [N,S,raw_stride] (channels 0..3 = r,g,b,density), t [N,S+1], rd = ray directions with
  * row stride rd_stride, noise [N,S] unit normal or NULL (density += noise*noise_std),

@@ -111,8 +111,11 @@ def main():
             buf.zero_()
             fn()
             torch.cuda.synchronize()
-            b = buf.view(148, 8).double()
+            b = buf.view(148, 8).double()[0::2]          # leader CTAs of the pairs
             tot, t_act, t_stage, e_wait, e_busy, n, e_pre, e_work = [b[:, i].mean().item() for i in range(8)]
+            if os.environ.get("DDNERF_TC_PROF_ISSUER"):
+                print(f"{name}: issuer total {tot:.0f} | act waits {100*t_act/tot:.1f}% | T0 passes {100*t_stage/tot:.1f}% | waits for own stages {100*e_wait/tot:.1f}% | waits for the peer's {100*e_busy/tot:.1f}%")
+                continue
             print(f"{name}: issuer total {tot:.0f} cyc | waits: epilogue {100 * t_act / tot:.1f}% ring {100 * t_stage / tot:.1f}% | "
                   f"epilogue busy {e_busy / max(n, 1):.0f} cyc each (store drain + barrier {e_pre / max(n, 1):.0f}, accumulator -> act buffer "
                   f"{e_work / max(n, 1):.0f}), waiting on MMA {e_wait / max(n, 1):.0f} cyc each, n={n:.0f}")
