@@ -37,6 +37,8 @@ def _stamp():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
+            if not os.path.isfile(os.path.join(root, name)):
+                continue
             with open(os.path.join(root, name), "rb") as f:
                 h.update(name.encode() + f.read())
     h.update(repr((BASE_FLAGS, SOURCES)).encode())
