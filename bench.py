@@ -311,8 +311,21 @@ def main():
     launches = lib.ddnerf_launch_count() - l0
     clocks = sampler.stop()
     mlp_events, ops.MLP_TIMING = ops.MLP_TIMING, None
-    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events)
     mlp_calls = len(mlp_events)
+    # time during which at least one MLP kernel was running (the weight-gradient kernel of one pass overlaps the
+    # dX chain of the next on a second stream): union of the event intervals on a common time base
+    mlp_ms = 0.0
+    if mlp_events:
+        t0 = mlp_events[0][0]
+        spans = sorted((t0.elapsed_time(a), t0.elapsed_time(b)) for a, b in mlp_events)
+        cur_lo, cur_hi = spans[0]
+        for lo, hi in spans[1:]:
+            if lo > cur_hi:
+                mlp_ms += cur_hi - cur_lo
+                cur_lo, cur_hi = lo, hi
+            else:
+                cur_hi = max(cur_hi, hi)
+        mlp_ms += cur_hi - cur_lo
 
     # ---- end-to-end arm: pinned host rays -> device every step, loss read back every step ----
     stage = [torch.empty_like(t, device=dev) for t in host[0]]

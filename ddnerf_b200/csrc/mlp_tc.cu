@@ -1015,7 +1015,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float
 
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const float* bias_pack, const float* grad_out,
                                                        int64_t rows, int out_channels, const void* mask_save, void* dz_save,
-                                                       void* stream) {
+                                                       int max_ctas, void* stream) {
     DDNERF_CHECK_ARG(wimg && bias_pack && grad_out && mask_save && dz_save, "mlp_tc_backward_dx: null pointer");
     DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_backward_dx: out_channels=%d (4 or 6)", out_channels);
     DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_backward_dx: the bf16 MLP needs an sm_100 device (tcgen05)");
@@ -1034,7 +1034,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const f
     g.C = out_channels;
     if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
     g.prof = g_prof_buffer;
-    const int grid = (int)std::min<int64_t>(n_items, sm_count());
+    int grid = (int)std::min<int64_t>(n_items, sm_count());
+    if (max_ctas > 0) grid = std::min(grid, max_ctas);
     mlp_tc_chain_kernel<1><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED("mlp_tc_backward_dx", 1);
     return 0;

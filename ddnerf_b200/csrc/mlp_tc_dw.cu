@@ -315,7 +315,7 @@ using namespace ddnerf;
 
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const void* enc_img,
                                                        const float* grad_out, const ddnerf_mlp_grads* grads, int64_t rows,
-                                                       int out_channels, void* stream) {
+                                                       int out_channels, int max_ctas, void* stream) {
     DDNERF_CHECK_ARG(act_save && dz_save && enc_img && grad_out && grads, "mlp_tc_backward_dw: null pointer");
     DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_backward_dw: out_channels=%d (4 or 6)", out_channels);
     for (int i = 0; i < (out_channels == 6 ? 13 : 12); ++i)
@@ -333,6 +333,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+    if (max_ctas > 0) sms = std::min(sms, max_ctas);
     DwWork work{};
     const int n_work = plan_work(n_tiles, sms, work);
     DwArgs g{};

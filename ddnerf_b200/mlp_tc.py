@@ -114,9 +114,9 @@ class _MlpTc(torch.autograd.Function):
         table = _ptr_table(gws, gbs)
         with _mlp_timer():
             _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(grad_out), rows, C, _p(ctx.mask), _p(dz),
-                                                     _stream()), "mlp_tc_backward_dx")
+                                                     0, _stream()), "mlp_tc_backward_dx")
             _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(ctx.act), _p(dz), _p(ctx.img), _p(grad_out), ctypes.byref(table), rows, C,
-                                                     _stream()), "mlp_tc_backward_dw")
+                                                     0, _stream()), "mlp_tc_backward_dw")
         ctx.img = ctx.act = ctx.mask = None
         return (None, None, None, None, *views)
 

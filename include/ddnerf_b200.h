@@ -125,13 +125,15 @@ int ddnerf_mlp_tc_forward(const void* wimg, const float* bias_pack, const void* 
  *     format as act_save), using the ReLU masks the training forward stored;
  * (2) the weight/bias gradients dW_l = dZ_l^T . A_{l-1}, db_l = colsum(dZ_l), ACCUMULATED with fp32
  *     atomics into `grads` (caller zeroes the buffers; [out,in] nn.Linear layout, any 4-byte
- *     alignment).  No gradient is produced for the encoded inputs (nothing upstream is trainable). */
+ *     alignment).  No gradient is produced for the encoded inputs (nothing upstream is trainable).
+ * max_ctas > 0 caps the number of CTAs (= SMs) a call occupies, so that the HBM-read-bound dW of one pass
+ * and the tensor/HBM-write-bound dX chain of the next can share the GPU from two streams; 0 = all SMs. */
 int ddnerf_mlp_tc_backward_dx(const void* wimg, const float* bias_pack, const float* grad_out,
                               int64_t rows, int out_channels, const void* mask_save,
-                              void* dz_save, void* stream);
+                              void* dz_save, int max_ctas, void* stream);
 int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const void* enc_img,
                               const float* grad_out, const ddnerf_mlp_grads* grads, int64_t rows,
-                              int out_channels, void* stream);
+                              int out_channels, int max_ctas, void* stream);
 
 /* Host-only consistency hooks (no device work): the static ring/op programs of the chain kernels
  * (0 = consistent) and the (layer-op, tile range) split of backward_dw over `sms` SMs, written as

@@ -82,10 +82,10 @@ def main():
         table = _ptr_table(gws, gbs)
 
         def dx():
-            _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(gout), rows, 4, _p(mask), _p(dz), _stream()), "dx")
+            _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(gout), rows, 4, _p(mask), _p(dz), 0, _stream()), "dx")
 
         def dw():
-            _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(act), _p(dz), _p(img), _p(gout), ctypes.byref(table), rows, 4, _stream()), "dw")
+            _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(act), _p(dz), _p(img), _p(gout), ctypes.byref(table), rows, 4, 0, _stream()), "dw")
 
         for name, fn, macs in (("dx", dx, 557696), ("dw", dw, 610304)):
             for _ in range(2):
