@@ -312,20 +312,10 @@ def main():
     clocks = sampler.stop()
     mlp_events, ops.MLP_TIMING = ops.MLP_TIMING, None
     mlp_calls = len(mlp_events)
-    # time during which at least one MLP kernel was running (the weight-gradient kernel of one pass overlaps the
-    # dX chain of the next on a second stream): union of the event intervals on a common time base
-    mlp_ms = 0.0
-    if mlp_events:
-        t0 = mlp_events[0][0]
-        spans = sorted((t0.elapsed_time(a), t0.elapsed_time(b)) for a, b in mlp_events)
-        cur_lo, cur_hi = spans[0]
-        for lo, hi in spans[1:]:
-            if lo > cur_hi:
-                mlp_ms += cur_hi - cur_lo
-                cur_lo, cur_hi = lo, hi
-            else:
-                cur_hi = max(cur_hi, hi)
-        mlp_ms += cur_hi - cur_lo
+    mlp_ms = sum(a.elapsed_time(b) for a, b, _ in mlp_events)
+    by_tag = {}
+    for a, b, tag in mlp_events:
+        by_tag.setdefault(tag, []).append(a.elapsed_time(b))
 
     # ---- end-to-end arm: pinned host rays -> device every step, loss read back every step ----
     stage = [torch.empty_like(t, device=dev) for t in host[0]]
@@ -367,6 +357,29 @@ def main():
                      "peak_kind": f"{pk_kind} bf16 sustained (MEASURED_PEAKS.json)",
                      "mlp_ms_per_step": mlp_ms / K if K else None},
     }
+    # per-kernel view of the MLP (CUDA events around each launch, averaged over the timed steps): the two chain
+    # kernels against the tensor roofline, the weight-gradient kernel against HBM (its algorithmic bytes: the
+    # saved tile images it has to read, 10.6 KB per sample row incl. the layer-5 / view-branch re-reads)
+    rows_step = n_rays * (cfg.nerf.train.num_coarse + cfg.nerf.train.num_fine)
+    algo = {"fwd": ("tensor", 2.0 * 610304 * rows_step, "TFLOP/s", peak_tf, 1e12),
+            "dx": ("tensor", 2.0 * 557696 * rows_step, "TFLOP/s", peak_tf, 1e12),
+            "dw": ("hbm", 1400.0 * 1024 / 128 * rows_step, "GB/s", pk["hbm_gbs"], 1e9)}
+    breakdown = []
+    for tag, (bound, work, unit, peak_v, scale) in algo.items():
+        if tag in by_tag:
+            ms_step = sum(by_tag[tag]) / K
+            ach = work / (ms_step * 1e-3) / scale
+            breakdown.append({"kernel": {"fwd": "mlp_tc_chain_kernel<0> (forward + activation saves)",
+                                         "dx": "mlp_tc_chain_kernel<1> (dX chain)", "dw": "mlp_tc_dw_kernel (dW, db)"}[tag],
+                              "bound": bound, "launches_per_step": len(by_tag[tag]) // K, "ms_per_step": ms_step,
+                              "achieved": ach, "peak": peak_v, "unit": unit, "frac": ach / peak_v})
+    if breakdown:
+        line["roofline"]["breakdown"] = breakdown
+        # DRAM bytes per step of the three MLP kernels from the committed ncu --set full captures
+        # (profiles/r01_ncu_mlp_tc_*.md: read + write per launch at 524,288 rows), scaled by rows
+        per_row = (2.90e9 + 2.76e9 + 5.81e9) / 524288.0
+        line["roofline"]["traffic"] = per_row * rows_step if args.mlp_mode == "bf16" else None
+        line["roofline"]["traffic_note"] = "dram__bytes_read+write of fwd/dx/dw from profiles/r01_ncu_mlp_tc_*.md, per step"
     if not args.no_render:
         line["render"] = run_render(args, dev, world, rank, dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -88,7 +88,7 @@ class _MlpTc(torch.autograd.Function):
         out = torch.empty(rows, C, device=dev, dtype=torch.float32)
         act = torch.empty(max(lib.ddnerf_mlp_tc_act_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
         mask = torch.empty(max(lib.ddnerf_mlp_tc_mask_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
-        with _mlp_timer():
+        with _mlp_timer("fwd"):
             _lib.check(lib.ddnerf_mlp_tc_forward(_p(st.wimg), _p(st.bias), _p(img), rows, C, _p(out), _p(act), _p(mask),
                                                  _stream()), "mlp_tc_forward")
         ctx.st, ctx.img, ctx.act, ctx.mask = st, img, act, mask
@@ -112,9 +112,10 @@ class _MlpTc(torch.autograd.Function):
         gws, gbs = views[:nw], views[nw:]
         dz = torch.empty(ctx.act.numel(), device=dev, dtype=torch.uint8)
         table = _ptr_table(gws, gbs)
-        with _mlp_timer():
+        with _mlp_timer("dx"):
             _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(grad_out), rows, C, _p(ctx.mask), _p(dz),
                                                      0, _stream()), "mlp_tc_backward_dx")
+        with _mlp_timer("dw"):
             _lib.check(lib.ddnerf_mlp_tc_backward_dw(_p(ctx.act), _p(dz), _p(ctx.img), _p(grad_out), ctypes.byref(table), rows, C,
                                                      0, _stream()), "mlp_tc_backward_dw")
         ctx.img = ctx.act = ctx.mask = None

@@ -15,6 +15,9 @@ MLP_TIMING = None
 
 
 class _mlp_timer:
+    def __init__(self, tag="mlp"):
+        self.tag = tag
+
     def __enter__(self):
         if MLP_TIMING is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -25,7 +28,7 @@ class _mlp_timer:
         if MLP_TIMING is not None and hasattr(self, "e0"):
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            MLP_TIMING.append((self.e0, e1))
+            MLP_TIMING.append((self.e0, e1, self.tag))
 
 
 def _stream():
