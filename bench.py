@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--mlp-mode", default=os.environ.get("DDNERF_MLP_MODE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame render leg (configs[2])")
     ap.add_argument("--render-frames", type=int, default=5)
     ap.add_argument("--render-chunk", type=int, default=0, help="rays per chunk of the render leg (0: one chunk per rank)")
@@ -272,7 +273,9 @@ def main():
     model.to(dev)
     for net in {id(model.coarse): model.coarse, id(model.fine): model.fine}.values():
         net.mlp_mode = args.mlp_mode
-    trainer = Trainer(model, distributed=world > 1)
+    # one CUDA graph per training step (single GPU; the NCCL all-reduce is kept out of graphs unless asked for)
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("DDNERF_GRAPH_DIST") == "1")
+    trainer = Trainer(model, distributed=world > 1, use_graph=use_graph)
     torch.manual_seed(1234 + rank)                                     # per-rank draws inside the path
 
     K, W = args.steps, max(args.warmup, 3)
@@ -301,18 +304,36 @@ def main():
     def step_resident(s):
         trainer.step(*resident[s % len(resident)])
 
-    for s in range(W):
-        step_resident(s)
-    ops.MLP_TIMING = []
+    l_before = lib.ddnerf_launch_count()
+    step_resident(0)                                                   # eager (graph warm-up): kernels of one step
+    launches_per_step = lib.ddnerf_launch_count() - l_before
+    try:
+        for s in range(1, max(W, Trainer.GRAPH_WARMUP + 1)):           # the last of these captures the graph
+            step_resident(s)
+        torch.cuda.synchronize()
+    except Exception as exc:                                           # capture refused: fall back to eager launches
+        if not trainer.use_graph:
+            raise
+        print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+        trainer.use_graph, trainer._graph = False, None
+        torch.cuda.synchronize()
+        for s in range(W):
+            step_resident(s)
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = lib.ddnerf_launch_count()
     ms_total = timed(step_resident, K)
-    launches = lib.ddnerf_launch_count() - l0
+    launches = launches_per_step * K                                   # (graph replays do not pass through the counter)
     clocks = sampler.stop()
+    # per-kernel CUDA-event timing of the MLP launches: events cannot be recorded inside a replayed graph, so the
+    # same steps are run eagerly (same kernels, same sizes) for the kernel-level numbers
+    K_ev = min(K, 20)
+    graphed, trainer.use_graph = trainer.use_graph, False
+    ops.MLP_TIMING = []
+    timed(step_resident, K_ev)
+    trainer.use_graph = graphed
     mlp_events, ops.MLP_TIMING = ops.MLP_TIMING, None
     mlp_calls = len(mlp_events)
-    mlp_ms = sum(a.elapsed_time(b) for a, b, _ in mlp_events)
+    mlp_ms = sum(a.elapsed_time(b) for a, b, _ in mlp_events) * (K / K_ev)     # scaled to the K timed steps
     by_tag = {}
     for a, b, tag in mlp_events:
         by_tag.setdefault(tag, []).append(a.elapsed_time(b))
@@ -345,7 +366,7 @@ def main():
         "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.mlp_mode == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": desc, "rays_per_gpu": n_rays, "mlp_mode": args.mlp_mode,
+        "config": {"workload": desc, "rays_per_gpu": n_rays, "mlp_mode": args.mlp_mode, "cuda_graph": bool(trainer.use_graph),
                    "l2": "per-step working set (activations + workspaces, GBs) far exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                 "ms_per_step": ms_e2e / K},
@@ -353,7 +374,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf_achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (tf_achieved / peak_tf) if tf_achieved else None, "traffic": None,
-                     "kernel": "NeRF MLP fwd+bwd (K1), %d calls/step" % (mlp_calls // max(K, 1)),
+                     "kernel": "NeRF MLP fwd+bwd (K1), %d launches/step; CUDA events over %d eagerly launched steps" % (mlp_calls // max(K_ev, 1), K_ev),
                      "peak_kind": f"{pk_kind} bf16 sustained (MEASURED_PEAKS.json)",
                      "mlp_ms_per_step": mlp_ms / K if K else None},
     }
@@ -367,11 +388,11 @@ def main():
     breakdown = []
     for tag, (bound, work, unit, peak_v, scale) in algo.items():
         if tag in by_tag:
-            ms_step = sum(by_tag[tag]) / K
+            ms_step = sum(by_tag[tag]) / K_ev
             ach = work / (ms_step * 1e-3) / scale
             breakdown.append({"kernel": {"fwd": "mlp_tc_chain_kernel<0> (forward + activation saves)",
                                          "dx": "mlp_tc_chain_kernel<1> (dX chain)", "dw": "mlp_tc_dw_kernel (dW, db)"}[tag],
-                              "bound": bound, "launches_per_step": len(by_tag[tag]) // K, "ms_per_step": ms_step,
+                              "bound": bound, "launches_per_step": len(by_tag[tag]) // K_ev, "ms_per_step": ms_step,
                               "achieved": ach, "peak": peak_v, "unit": unit, "frac": ach / peak_v})
     if breakdown:
         line["roofline"]["breakdown"] = breakdown

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ddnerf_dp_loss_backward": (c_i, [c_p] * 8 + [c_i] + [c_p] * 5 + [c_l, c_i, c_i, c_p]),
     "ddnerf_mse_loss": (c_i, [c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_p]),
     "ddnerf_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_i, c_f, c_p]),
+    "ddnerf_adam_step_dev": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p]),
 }
 
 _lib = None

@@ -52,6 +52,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// same update with the scalars read from device memory: lets a CUDA graph of the whole step be replayed while
+// the learning rate and the bias corrections change from step to step
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                int64_t n, const float* __restrict__ hyper) {
+    const float lr = __ldg(hyper), b1 = __ldg(hyper + 1), b2 = __ldg(hyper + 2), eps = __ldg(hyper + 3);
+    const float bc1 = __ldg(hyper + 4), bc2_sqrt = __ldg(hyper + 5), gscale = __ldg(hyper + 6);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float gr = __ldg(g + e) * gscale;
+        float mm = m[e] + (gr - m[e]) * (1.0f - b1);
+        float vv = v[e] * b2 + (1.0f - b2) * gr * gr;
+        m[e] = mm; v[e] = vv;
+        float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] -= (lr / bc1) * (mm / denom);
+    }
+}
+
 }  // namespace
 }  // namespace ddnerf
 
@@ -81,5 +97,15 @@ extern "C" DDNERF_EXPORT int ddnerf_adam_step(float* param, const float* grad, f
     adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                         eps, bc1, bc2_sqrt, grad_scale);
     DDNERF_LAUNCHED("adam_step", 1);
+    return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    const float* hyper, void* stream) {
+    DDNERF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper, "adam_step_dev: null pointer");
+    if (n == 0) return 0;
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    adam_dev_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper);
+    DDNERF_LAUNCHED("adam_step_dev", 1);
     return 0;
 }

@@ -44,14 +44,21 @@ class FlatBucket:
         for p in self.params:
             p.grad = None
 
-    def adam(self, lr, grad_scale=1.0):
-        self.step += 1
-        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step, grad_scale=grad_scale)
-        # the kernel writes through raw pointers (no autograd version bump): tell the bf16 path that its
-        # packed weight images are stale
+    def mark_dirty(self):
+        """The optimizer kernels write through raw pointers (no autograd version bump): tell the bf16 path
+        that its packed weight images are stale."""
         st = getattr(self.module, "_tc_state", None)
         if st is not None:
             st.dirty = True
+
+    def adam(self, lr, grad_scale=1.0):
+        self.step += 1
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step, grad_scale=grad_scale)
+        self.mark_dirty()
+
+    def adam_dev(self, hyper):
+        """Same update with its scalars in device memory (graph capture); the caller advances `step`."""
+        ops.adam_step_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, hyper)
 
 
 def shard_rows(n_rows, rank, world):
@@ -71,9 +78,18 @@ def allreduce_gradients(buckets, world):
 
 
 class Trainer:
-    """Drives ``model.run_iter`` + loss + backward + (all-reduce) + Adam, one call per iteration."""
+    """Drives ``model.run_iter`` + loss + backward + (all-reduce) + Adam, one call per iteration.
 
-    def __init__(self, model, train_iters=200001, distributed=None):
+    ``use_graph=True`` captures the whole iteration (about 160 kernel launches and as many host-side
+    dispatches) into ONE CUDA graph after two eager iterations and replays it from then on; the values that
+    change every iteration -- learning rate, Adam bias corrections, the annealed ``gaussian_smooth_factor`` --
+    live in device memory and are refreshed by copy nodes inside the graph.  The graph is re-captured when
+    ``pdf_padding`` flips (train_model.py:140-142) or the batch shape changes.  The results are those of the
+    eager path: the same kernels in the same order."""
+
+    GRAPH_WARMUP = 2
+
+    def __init__(self, model, train_iters=200001, distributed=None, use_graph=False):
         self.model = model
         self.cfg = model.cfg
         self.is_dd = self.cfg.nerf.type == "DDNerfModel"
@@ -88,20 +104,30 @@ class Trainer:
         self._smooth0 = tp.gaussian_smooth_factor
         self._dsmooth = (tp.gaussian_smooth_factor - tp.final_smooth) / tp.finnish_smooth
         model.record_distributions = False
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._graph_key = None
+        self._static = None
+        dev = self.buckets[0].flat.device
+        if self.use_graph:
+            # [lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, gaussian_smooth_factor]
+            self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(8, device=dev, dtype=torch.float32)
 
     def lr(self, i):
         return learning_rate_decay(i, 0.0005, 5e-6, self.train_iters, lr_delay_steps=2500, lr_delay_mult=0.01)
 
-    def step(self, ray_origins, ray_directions, ray_rad, target):
-        """train_model.py:135-177 for one iteration.  Returns (loss, mse[2]) as device tensors (no
-        host sync)."""
-        i, tp = self.iter, self.cfg.train_params
-        if i < tp.finnish_smooth:                                # train_model.py:135-138
-            tp.gaussian_smooth_factor = self._smooth0 - self._dsmooth * i
-        else:
-            tp.gaussian_smooth_factor = tp.final_smooth
+    def _schedule(self, i):
+        """Per-iteration host scalars of the driver loop (train_model.py:135-150)."""
+        tp = self.cfg.train_params
+        smooth = self._smooth0 - self._dsmooth * i if i < tp.finnish_smooth else tp.final_smooth
         if i == tp.max_pdf_pad_iters:
             tp.pdf_padding = False
+        return smooth, self.lr(i)
+
+    def _body(self, ray_origins, ray_directions, ray_rad, target, lr, hyper=None):
+        """One iteration on the current stream: run_iter, losses, backward, gradient all-reduce, Adam."""
+        tp = self.cfg.train_params
         self.model.train()
         out = self.model.run_iter(ray_origins, ray_directions, ray_rad, mode="train", rgb_target=target)
         coef = tp.loss_coeficients
@@ -114,11 +140,63 @@ class Trainer:
             tensors.append(dp)
             grads.append(torch.full_like(dp, tp.dp_coeficient))
         torch.autograd.backward(tensors, grads)
-        lr = self.lr(i)
         for b in self.buckets:
             b.gather_grads()
         allreduce_gradients(self.buckets, self.world if self.distributed else 1)
         for b in self.buckets:
-            b.adam(lr, grad_scale=1.0 / self.world)
-        self.iter += 1
+            if hyper is None:
+                b.adam(lr, grad_scale=1.0 / self.world)
+            else:
+                b.adam_dev(hyper)
         return loss, mse
+
+    def step(self, ray_origins, ray_directions, ray_rad, target):
+        """train_model.py:135-177 for one iteration.  Returns (loss, mse[2]) as device tensors (no
+        host sync)."""
+        i, tp = self.iter, self.cfg.train_params
+        smooth, lr = self._schedule(i)
+        if not self.use_graph or i < self.GRAPH_WARMUP:
+            tp.gaussian_smooth_factor = smooth
+            loss, mse = self._body(ray_origins, ray_directions, ray_rad, target, lr)
+            self.iter += 1
+            return loss, mse
+
+        # ---- graphed iteration ------------------------------------------------------------------
+        t = i + 1                                              # Adam step count of this iteration (all buckets in lock step)
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3] = lr, 0.9, 0.999, 1e-8
+        h[4], h[5] = 1.0 - 0.9 ** t, math.sqrt(1.0 - 0.999 ** t)
+        h[6], h[7] = 1.0 / self.world, smooth
+        key = (bool(tp.pdf_padding), tuple(ray_origins.shape), tuple(target.shape), ray_origins.device)
+        if self._graph is None or key != self._graph_key:
+            self._capture(key, ray_origins, ray_directions, ray_rad, target, lr)
+        for dst, src in zip(self._static["in"], (ray_origins, ray_directions, ray_rad, target)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        for b in self.buckets:
+            b.step += 1
+            b.mark_dirty()
+        self.iter += 1
+        return self._static["loss"], self._static["mse"]
+
+    def _capture(self, key, ray_origins, ray_directions, ray_rad, target, lr):
+        tp = self.cfg.train_params
+        self._static = {"in": [torch.empty_like(x) for x in (ray_origins, ray_directions, ray_rad, target)]}
+        for dst, src in zip(self._static["in"], (ray_origins, ray_directions, ray_rad, target)):
+            dst.copy_(src)
+        for b in self.buckets:
+            for p in b.params:
+                p.grad = None
+            b.mark_dirty()                                     # the graph re-packs the bf16 weight images every replay
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        smooth_dev = self._hyper_dev[7]                        # 0-dim view: `sigmas * gaussian_smooth_factor` reads device memory
+        saved = tp.gaussian_smooth_factor
+        with torch.cuda.graph(graph):
+            self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            tp.gaussian_smooth_factor = smooth_dev if self.is_dd else saved
+            loss, mse = self._body(*self._static["in"], lr, hyper=self._hyper_dev)
+        tp.gaussian_smooth_factor = float(saved) if not isinstance(saved, torch.Tensor) else float(self._hyper_host[7])
+        self._static["loss"], self._static["mse"] = loss, mse
+        self._graph, self._graph_key = graph, key

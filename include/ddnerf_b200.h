@@ -206,6 +206,12 @@ int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp
                      int64_t n, float lr, float beta1, float beta2, float eps, int step,
                      float grad_scale, void* stream);
 
+/* The same update with its scalars in device memory: hyper[7] = {lr, beta1, beta2, eps, 1 - beta1^step,
+ * sqrt(1 - beta2^step), grad_scale}.  Lets a CUDA graph of the whole training step be replayed while the
+ * learning rate and bias corrections change every step. */
+int ddnerf_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                         int64_t n, const float* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
