@@ -258,8 +258,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout; stdout carries one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            # the NCCL version banner (NCCL_DEBUG=VERSION, from the environment or nccl.conf) goes to stdout;
+            # stdout carries exactly one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     os.environ["DDNERF_MLP_MODE"] = args.mlp_mode
@@ -273,8 +275,8 @@ def main():
     model.to(dev)
     for net in {id(model.coarse): model.coarse, id(model.fine): model.fine}.values():
         net.mlp_mode = args.mlp_mode
-    # one CUDA graph per training step (single GPU; the NCCL all-reduce is kept out of graphs unless asked for)
-    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("DDNERF_GRAPH_DIST") == "1")
+    # one CUDA graph per training step (with several ranks: two graphs around the eagerly launched NCCL all-reduce)
+    use_graph = not args.no_graph
     trainer = Trainer(model, distributed=world > 1, use_graph=use_graph)
     torch.manual_seed(1234 + rank)                                     # per-rank draws inside the path
 

@@ -106,6 +106,7 @@ class Trainer:
         model.record_distributions = False
         self.use_graph = bool(use_graph)
         self._graph = None
+        self._graph_tail = None
         self._graph_key = None
         self._static = None
         dev = self.buckets[0].flat.device
@@ -142,13 +143,18 @@ class Trainer:
         torch.autograd.backward(tensors, grads)
         for b in self.buckets:
             b.gather_grads()
+        if hyper is not None and self.distributed and self.world > 1:
+            return loss, mse                                     # graph mode: the collective and Adam follow outside
         allreduce_gradients(self.buckets, self.world if self.distributed else 1)
+        self._optimize(lr, hyper)
+        return loss, mse
+
+    def _optimize(self, lr, hyper=None):
         for b in self.buckets:
             if hyper is None:
                 b.adam(lr, grad_scale=1.0 / self.world)
             else:
                 b.adam_dev(hyper)
-        return loss, mse
 
     def step(self, ray_origins, ray_directions, ray_rad, target):
         """train_model.py:135-177 for one iteration.  Returns (loss, mse[2]) as device tensors (no
@@ -174,6 +180,9 @@ class Trainer:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        if self._graph_tail is not None:                       # data parallel: NCCL all-reduce between two graphs
+            allreduce_gradients(self.buckets, self.world)
+            self._graph_tail.replay()
         for b in self.buckets:
             b.step += 1
             b.mark_dirty()
@@ -199,4 +208,12 @@ class Trainer:
             loss, mse = self._body(*self._static["in"], lr, hyper=self._hyper_dev)
         tp.gaussian_smooth_factor = float(saved) if not isinstance(saved, torch.Tensor) else float(self._hyper_host[7])
         self._static["loss"], self._static["mse"] = loss, mse
+        self._graph_tail = None
+        if self.distributed and self.world > 1:                # the collective is launched eagerly between two graphs
+            allreduce_gradients(self.buckets, self.world)
+            torch.cuda.synchronize()
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail, pool=graph.pool()):
+                self._optimize(lr, hyper=self._hyper_dev)
+            self._graph_tail = tail
         self._graph, self._graph_key = graph, key
