@@ -21,7 +21,7 @@ BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # so their rounding follows the reference's op-by-op fp32 arithmetic; the GEMM files keep it.
 SOURCES = {
     "api.cu": [],
-    "composite.cu": ["-fmad=false"],
+    "composite.cu": [],
     "sampler.cu": ["-fmad=false"],
     "encode.cu": ["-fmad=false"],
     "dploss.cu": ["-fmad=false"],

@@ -95,6 +95,19 @@ __device__ __forceinline__ float normal_cdff_(float x) {
     return 0.5f * (1.0f + erff(x / 1.41421354f));      // math_utils.py:193-200, sqrt(2) in fp32
 }
 
+// ---- SFU helpers (MUFU ex2 / lg2 / rcp, <= 2 ulp) ------------------------------------------------
+__device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+// a / b for normal-range b: reciprocal + one residual correction = the correctly rounded quotient except in
+// rare double-rounding cases; no special-case slow path (0/0 and x/0 give NaN, callers handle it).
+__device__ __forceinline__ float div_fast(float a, float b) {
+    float r = rcp_(b);
+    float q = a * r;
+    return fmaf(fmaf(-q, b, a), r, q);
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace ddnerf

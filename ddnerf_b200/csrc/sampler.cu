@@ -8,6 +8,8 @@
 // binary-searches it per sample: O(S + n log S) work and bins+weights+u in, samples out of HBM.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ddnerf {
@@ -16,21 +18,75 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // sample_first_cycle: elementwise
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float linspace01(int idx, int steps) {     // torch.linspace(0,1,steps)[idx]
-    float step = 1.0f / (float)(steps - 1);
+__device__ __forceinline__ float linspace01(int idx, int steps, float step) {   // torch.linspace(0,1,steps)[idx]
     return idx < steps / 2 ? step * (float)idx : 1.0f - step * (float)(steps - idx - 1);
 }
 
-__global__ void first_cycle_kernel(const float* __restrict__ near, const float* __restrict__ far, int64_t ray_stride,
-                                   const float* __restrict__ t_rand, float* __restrict__ out, int64_t N, int S,
-                                   int lindisp) {
+// One warp per ray, lanes stride over the S+1 fence-posts (coalesced, no integer division).  The jitter
+// needs the neighbouring fence-posts: they come from the adjacent lanes by shuffle; the two lanes at the
+// chunk edges take them from the previous chunk's last / the next chunk's first value.  All of a ray's
+// random numbers are requested before the first is used (K chunks, compile time), otherwise the kernel is
+// bound by one DRAM latency per chunk.
+template <int K>
+__global__ void __launch_bounds__(256) first_cycle_kernel(const float* __restrict__ near, const float* __restrict__ far,
+                                                           int64_t ray_stride, const float* __restrict__ t_rand,
+                                                           float* __restrict__ out, int64_t N, int S, int lindisp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= N) return;
+    const int steps = S + 1;
+    const float* rr = t_rand ? t_rand + ray * steps : nullptr;
+    float rnd[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) rnd[c] = (rr && c * 32 + lane <= S) ? __ldg(rr + c * 32 + lane) : 0.f;
+    const float nr = __ldg(near + ray * ray_stride), fr = __ldg(far + ray * ray_stride);
+    const float step = 1.0f / (float)S;
+    const float inr = lindisp ? 1.0f / nr : 0.f, ifr = lindisp ? 1.0f / fr : 0.f;
+    auto tv = [&](int k) {
+        k = min(max(k, 0), S);
+        float s = linspace01(k, steps, step);
+        return lindisp ? 1.0f / (inr * (1.0f - s) + ifr * s) : nr * (1.0f - s) + fr * s;
+    };
+    float* orow = out + ray * steps;
+    float cur = tv(lane), prev_last = cur;              // prev_last: value at index (chunk start - 1)
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const int i = c * 32 + lane;
+        if (c * 32 > S) break;
+        const float nxt_chunk = tv(i + 32);             // next chunk's values (clamped index)
+        float lo_n = __shfl_up_sync(FULL, cur, 1);      // t[i-1]
+        float hi_n = __shfl_down_sync(FULL, cur, 1);    // t[i+1]
+        const float next_first = __shfl_sync(FULL, nxt_chunk, 0);
+        if (lane == 0) lo_n = prev_last;
+        if (lane == 31) hi_n = next_first;
+        prev_last = __shfl_sync(FULL, cur, 31);
+        if (i <= S) {
+            float t = cur;
+            if (rr) {                                   // samplers.py:52-60
+                float lower = i == 0 ? cur : 0.5f * (cur + lo_n);
+                float upper = i == S ? cur : 0.5f * (hi_n + cur);
+                t = lower + (upper - lower) * rnd[c];
+                if (i == 0) t = nr;
+                if (i == S) t = fr;
+            }
+            orow[i] = t;
+        }
+        cur = nxt_chunk;
+    }
+}
+
+// any S: element-parallel (no prefetch)
+__global__ void first_cycle_generic_kernel(const float* __restrict__ near, const float* __restrict__ far, int64_t ray_stride,
+                                           const float* __restrict__ t_rand, float* __restrict__ out, int64_t N, int S,
+                                           int lindisp) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N * (S + 1)) return;
     int64_t ray = e / (S + 1);
     int i = (int)(e - ray * (S + 1));
     const float nr = __ldg(near + ray * ray_stride), fr = __ldg(far + ray * ray_stride);
+    const float step = 1.0f / (float)S;
     auto tv = [&](int k) {
-        float s = linspace01(k, S + 1);
+        float s = linspace01(k, S + 1, step);
         return lindisp ? 1.0f / (1.0f / nr * (1.0f - s) + 1.0f / fr * s) : nr * (1.0f - s) + fr * s;
     };
     float t = tv(i);
@@ -105,6 +161,204 @@ __device__ __forceinline__ float make_u(const USpec& us, int k, int n, const flo
     u = fminf(u, 0.9999f);
     if (us.clamp0) u = fmaxf(u, 0.0f);
     return u;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path (S <= 256): G lanes per ray, C consecutive cells per lane (G*C >= S, a power of two).
+//   * the smoothed pdf lives in registers; its CDF is a per-lane serial sum plus ONE lane-group scan, both
+//     in double (monotone, ties exact -- what torch.cumsum on the CPU produces), instead of one scan per
+//     32 cells;
+//   * {cdf, bin} pairs are staged once in shared memory (8 B per fence-post);
+//   * each sample's interval comes from a branch-free binary search, log2(G*C) predicated steps;
+//   * divisions are reciprocal + one residual correction (div_fast), no slow path.
+// Round-1 profile of the generic kernels below: 313 thread instructions per sample, issue-active 88 %
+// (profiles/r01_ncu_sample_pdf_*.md); they remain the fallback for S > 256.
+// ------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ double group_incl_sum_d2(double v, int gl) { return group_incl_sum_d<G>(v, gl); }
+
+template <int G, int C>
+struct FastCdf {
+    static constexpr int P = G * C;                       // searched positions 1..P-1
+    // cb[0..P]: x = cdf, y = bin.  Entries S+1..P hold +inf / 0.
+    __device__ static __forceinline__ void build(const float* __restrict__ w_row, const float* __restrict__ bins_row,
+                                                 float2* cb, int S, int gl, int pdf_padding) {
+        float w[C];
+        const int e0 = gl * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = __ldg(w_row + min(e0 + c, S - 1));
+        for (int q = gl; q <= P; q += G) {
+            cb[q].y = q <= S ? __ldg(bins_row + q) : 0.f;
+            if (q > S) cb[q].x = __int_as_float(0x7f800000);
+        }
+        float prev = __shfl_up_sync(FULL, w[C - 1], 1, G);
+        float next = __shfl_down_sync(FULL, w[0], 1, G);
+        if (gl == 0) prev = w[0];                         // samplers.py:70-72 replicate padding
+        if (gl == G - 1) next = w[C - 1];
+        float v[C], part = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float p = c ? w[c > 0 ? c - 1 : 0] : prev, nx = c < C - 1 ? w[c < C - 1 ? c + 1 : 0] : next, cur = w[c];
+            float x;
+            if (pdf_padding) x = 0.5f * (fmaxf(p, cur) + fmaxf(cur, nx)) + 0.01f;
+            else x = 0.8f * cur + 0.1f * p + 0.1f * nx + 0.01f;
+            v[c] = e0 + c < S ? x : 0.f;
+            part += v[c];
+        }
+        const float total = group_sum<G>(part);
+        double incl[C], run = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { run += (double)div_fast(v[c], total); incl[c] = run; }
+        double lanes_incl = group_incl_sum_d<G>(run, gl);
+        double off = __shfl_up_sync(FULL, lanes_incl, 1, G);
+        if (gl == 0) off = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int m = e0 + c + 1;                     // cdf[m] = min(1, sum_{i<m} pdf_i), m = 1..S-1
+            if (m <= S - 1) cb[m].x = fminf(1.0f, (float)(off + incl[c]));
+        }
+        if (gl == 0) { cb[0].x = 0.f; cb[S].x = 1.f; }
+        __syncwarp();
+    }
+    // j = #{m in [0,S] : cdf[m] <= u} - 1  (u >= 0)
+    __device__ static __forceinline__ int search(const float2* cb, int S, float u) {
+        int pos = 0;
+#pragma unroll
+        for (int step = P / 2; step >= 1; step /= 2)
+            if (cb[pos + step].x <= u) pos += step;
+        if (S == P && u >= 1.0f) pos = S;                 // position P (= S) is outside the searched range
+        return pos;
+    }
+};
+
+struct UGen {
+    float det_step; USpec us; int n;
+    __device__ UGen(const USpec& u, int n_) : us(u), n(n_) { det_step = us.hi / (float)(n - 1); }
+    __device__ __forceinline__ float operator()(int k, float rnd) const {
+        if (us.det) return k < n / 2 ? det_step * (float)k : us.hi - det_step * (float)(n - k - 1);
+        float u = (float)k * us.stride + div_fast(rnd, us.div);
+        u = fminf(u, 0.9999f);
+        if (us.clamp0) u = fmaxf(u, 0.0f);
+        return u;
+    }
+};
+
+// K: output chunks per lane (n <= K*G).  Every global load of the ray -- weights, bins, the K random numbers --
+// is requested before the first dependent instruction; the kernels are otherwise bound by one DRAM latency
+// per chunk.
+template <int G, int C, int K>
+__global__ void __launch_bounds__(256) sample_pdf_fast_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                               const float* __restrict__ rand, float* __restrict__ out,
+                                                               int32_t* __restrict__ idx_out, int64_t N, int S, int n,
+                                                               int pdf_padding, USpec us) {
+    using F = FastCdf<G, C>;
+    __shared__ float2 cbs[256 / G][F::P + 1];
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    int64_t ray = (int64_t)blockIdx.x * (256 / G) + grp;
+    const bool valid = ray < N;
+    if (!valid) ray = N - 1;                                             // keep the warp convergent for the shuffles
+    float2* cb = cbs[grp];
+    float rnd[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) rnd[c] = (rand && c * G + gl < n) ? __ldg(rand + ray * n + c * G + gl) : 0.f;
+    F::build(weights + ray * S, bins + ray * (S + 1), cb, S, gl, pdf_padding);
+    if (!valid) return;
+    const UGen ugen(us, n);
+    float* orow = out + ray * n;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const int k = c * G + gl;
+        if (k >= n) break;
+        const float u = ugen(k, rnd[c]);
+        const int j = F::search(cb, S, u);
+        const float2 a0 = cb[j], a1 = cb[min(j + 1, S)];
+        float t = div_fast(u - a0.x, a1.x - a0.x);
+        if (t != t) t = 0.f;                                             // nan_to_num(., 0)
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        orow[k] = a0.y + t * (a1.y - a0.y);
+        if (idx_out) idx_out[ray * n + k] = j;
+    }
+}
+
+template <int G, int C, int K>
+__global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
+    const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ mus,
+    const float* __restrict__ sigmas, const float* __restrict__ part_inside, const float* __restrict__ left_tail,
+    const float* __restrict__ rand, float* __restrict__ out, int32_t* __restrict__ idx_out, int64_t N, int S, int n,
+    int pdf_padding, float near_cfg, float far_cfg, USpec us) {
+    using F = FastCdf<G, C>;
+    __shared__ float2 cbs[256 / G][F::P + 1];
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    int64_t ray = (int64_t)blockIdx.x * (256 / G) + grp;
+    const bool valid = ray < N;
+    if (!valid) ray = N - 1;
+    float2* cb = cbs[grp];
+    float rnd[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) rnd[c] = (rand && c * G + gl < n) ? __ldg(rand + ray * n + c * G + gl) : 0.f;
+    F::build(weights + ray * S, bins + ray * (S + 1), cb, S, gl, pdf_padding);
+    const float* mu_r = mus + ray * S;
+    const float* sg_r = sigmas + ray * S;
+    const float* pin_r = part_inside + ray * S;
+    const float* lt_r = left_tail + ray * S;
+    const UGen ugen(us, n);
+    float* orow = out + ray * n;
+    bool ok = true;
+    float prev_last = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {                                        // uniform trip count over the warp
+        const int k = c * G + gl;
+        if (c * G >= n) break;
+        const bool in = k < n;
+        float val = __int_as_float(0x7f800000);
+        if (in) {
+            const float u = ugen(k, rnd[c]);
+            float z, b0, b1;
+            int ind;
+            if (S == 1) {                                                // samplers.py:185-190
+                ind = 0; b0 = cb[0].y; b1 = cb[1].y;
+                z = u * __ldg(pin_r) + __ldg(lt_r);
+            } else {
+                const int j = F::search(cb, S, u);
+                const float2 a0 = cb[j], a1 = cb[min(j + 1, S)];
+                b0 = a0.y; b1 = a1.y;
+                ind = j;                                                 // torch.max: first index of the maximum
+                while (ind > 0 && cb[ind - 1].y == cb[ind].y) --ind;
+                ind = min(ind, S - 1);
+                z = div_fast(u - a0.x, a1.x - a0.x) * __ldg(pin_r + ind) + __ldg(lt_r + ind);
+                z = fminf(z, 0.999f);
+            }
+            z = 1.41421354f * erfinvf(2.0f * z - 1.0f);                  // math_utils.py:202-208
+            float t = fminf(fmaxf(z * __ldg(sg_r + ind) + __ldg(mu_r + ind), 0.f), 0.99999f);
+            val = b0 + t * (b1 - b0);
+            if (k == 0) val = near_cfg;                                  // samplers.py:210-211
+            if (k == n - 1) val = far_cfg;
+            if (valid) {
+                orow[k] = val;
+                if (idx_out) idx_out[ray * n + k] = ind;
+            }
+        }
+        // samplers.py:213 sorts; the samples are monotone by construction unless bins leave [near_cfg, far_cfg]
+        float nb = __shfl_down_sync(FULL, val, 1, G);
+        if (gl == G - 1) nb = __int_as_float(0x7f800000);
+        if (val > nb) ok = false;
+        if (gl == 0 && prev_last > val) ok = false;
+        prev_last = __shfl_sync(FULL, val, G - 1, G);
+    }
+    // any lane of the group saw an inversion -> lane 0 of the group insertion-sorts the row in place
+    unsigned bad = __ballot_sync(FULL, !ok);
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
+    if ((bad & gmask) && valid) {
+        __syncwarp(gmask);
+        if (gl == 0) {
+            for (int a = 1; a < n; ++a) {
+                float x = orow[a];
+                int b = a - 1;
+                while (b >= 0 && orow[b] > x) { orow[b + 1] = orow[b]; --b; }
+                orow[b + 1] = x;
+            }
+        }
+    }
 }
 
 __global__ void sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
@@ -220,6 +474,21 @@ __global__ void find_interval_kernel(const float* __restrict__ cdf, const float*
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// (G lanes per ray, C cells per lane, K output chunks per lane) of the fast path; false -> generic kernels
+template <typename F>
+bool dispatch_fast(int S, int n, F&& f) {
+#define DDNERF_FAST(G, C)                                                                                                   \
+    if (S <= G * C) {                                                                                                       \
+        if (n <= 5 * G) { f(std::integral_constant<int, G>{}, std::integral_constant<int, C>{}, std::integral_constant<int, 5>{}); return true; } \
+        if (n <= 9 * G) { f(std::integral_constant<int, G>{}, std::integral_constant<int, C>{}, std::integral_constant<int, 9>{}); return true; } \
+        return false;                                                                                                       \
+    }
+    // eight cells per lane wherever S allows: short rays share a warp
+    DDNERF_FAST(4, 1) DDNERF_FAST(4, 2) DDNERF_FAST(4, 4) DDNERF_FAST(4, 8) DDNERF_FAST(8, 8) DDNERF_FAST(16, 8) DDNERF_FAST(32, 8)
+#undef DDNERF_FAST
+    return false;
+}
+
 }  // namespace
 }  // namespace ddnerf
 
@@ -230,9 +499,11 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_first_cycle(const float* near, const 
     DDNERF_CHECK_ARG(near && far && t_out, "sample_first_cycle: null pointer");
     DDNERF_CHECK_ARG(S >= 1, "sample_first_cycle: S=%d < 1", S);
     if (N == 0) return 0;
-    int64_t total = N * (S + 1);
-    first_cycle_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(near, far, ray_stride, t_rand,
-                                                                                            t_out, N, S, lindisp);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (S + 1 <= 32 * 2) first_cycle_kernel<2><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    else if (S + 1 <= 32 * 5) first_cycle_kernel<5><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    else if (S + 1 <= 32 * 9) first_cycle_kernel<9><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    else first_cycle_generic_kernel<<<ceil_div(N * (S + 1), 256), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
     DDNERF_LAUNCHED("sample_first_cycle", 1);
     return 0;
 }
@@ -249,12 +520,19 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf(const float* bins, const float* w
     if (N == 0) return 0;
     double s = 1.0 / n;
     USpec us{rand == nullptr, 1.0f, (float)s, (float)((1.0 / s) + 1e-5), 0};
-    int per_warp = (S + 2) + S + (S + 1) + (S + 1);
-    int wpb = warps_per_block(per_warp);
-    DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf: S=%d needs too much shared memory", S);
-    sample_pdf_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float),
-                        static_cast<cudaStream_t>(stream)>>>(bins, weights, rand, out, idx_out, N, S, n, pdf_padding, us,
-                                                             per_warp);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool fast = dispatch_fast(S, n, [&](auto g, auto c, auto kk) {
+        constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
+        sample_pdf_fast_kernel<G, C, K><<<ceil_div(N, 256 / G), 256, 0, st>>>(bins, weights, rand, out, idx_out, N, S, n,
+                                                                          pdf_padding, us);
+    });
+    if (!fast) {
+        int per_warp = (S + 2) + S + (S + 1) + (S + 1);
+        int wpb = warps_per_block(per_warp);
+        DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf: S=%d needs too much shared memory", S);
+        sample_pdf_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(
+            bins, weights, rand, out, idx_out, N, S, n, pdf_padding, us, per_warp);
+    }
     DDNERF_LAUNCHED("sample_pdf", 1);
     return 0;
 }
@@ -269,14 +547,22 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const
     if (N == 0) return 0;
     double s = 1.0 / (n - 1);
     USpec us{rand == nullptr, 0.9999f, (float)s, (float)(n + 1e-5), 1};
-    int np2 = next_pow2(n);
-    int per_warp = (S + 2) + S + (S + 1) + (S + 1) + np2;
-    int wpb = warps_per_block(per_warp);
-    DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf_mu_sigma: S=%d n=%d needs too much shared memory", S, n);
-    sample_pdf_mu_sigma_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float),
-                                 static_cast<cudaStream_t>(stream)>>>(bins, weights, mus, sigmas, part_inside, left_tail,
-                                                                      rand, out, idx_out, N, S, n, np2, pdf_padding,
-                                                                      near_cfg, far_cfg, us, per_warp);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool fast = dispatch_fast(S, n, [&](auto g, auto c, auto kk) {
+        constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
+        sample_pdf_mu_sigma_fast_kernel<G, C, K><<<ceil_div(N, 256 / G), 256, 0, st>>>(
+            bins, weights, mus, sigmas, part_inside, left_tail, rand, out, idx_out, N, S, n, pdf_padding, near_cfg, far_cfg,
+            us);
+    });
+    if (!fast) {
+        int np2 = next_pow2(n);
+        int per_warp = (S + 2) + S + (S + 1) + (S + 1) + np2;
+        int wpb = warps_per_block(per_warp);
+        DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf_mu_sigma: S=%d n=%d needs too much shared memory", S, n);
+        sample_pdf_mu_sigma_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(
+            bins, weights, mus, sigmas, part_inside, left_tail, rand, out, idx_out, N, S, n, np2, pdf_padding, near_cfg,
+            far_cfg, us, per_warp);
+    }
     DDNERF_LAUNCHED("sample_pdf_mu_sigma", 1);
     return 0;
 }
