@@ -108,6 +108,30 @@ __device__ __forceinline__ float div_fast(float a, float b) {
     return fmaf(fmaf(-q, b, a), r, q);
 }
 
+// Branch-free binary search over a shared-memory table of REC-byte records (positions 1 .. 2*STEP-1): one
+// shared load, one compare and one predicated add per step -- the running position is a byte address and the
+// step an immediate offset of the load.  M independent searches advance in lock step so that their shared-
+// memory latencies overlap (one search alone is a chain of log2(P) dependent loads).  STRICT: count keys < x,
+// else keys <= x.  at[m] enters as the shared address of record 0's key and leaves as the address of record
+// (count)'s key.
+template <int STEP, bool STRICT, int M, int REC>
+struct SmemSearch {
+    __device__ static __forceinline__ void run(unsigned (&at)[M], const float (&x)[M]) {
+        float v[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[m]) : "r"(at[m]), "n"(STEP * REC) : "memory");
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (STRICT ? (v[m] < x[m]) : (v[m] <= x[m])) at[m] += STEP * REC;
+        SmemSearch<STEP / 2, STRICT, M, REC>::run(at, x);
+    }
+};
+template <bool STRICT, int M, int REC>
+struct SmemSearch<0, STRICT, M, REC> {
+    __device__ static __forceinline__ void run(unsigned (&)[M], const float (&)[M]) {}
+};
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace ddnerf

@@ -206,142 +206,195 @@ __global__ void dp_loss_bwd_kernel(DpArgs a, const float* __restrict__ g_loss, c
 }
 
 // ------------------------------------------------------------------------------------------
-// Fast path (S0 <= 256): G lanes per ray, C consecutive coarse cells per lane (G*C >= S0, a power of two).
-// Same scheme as the fast resamplers (sampler.cu): blocked double-precision CDF with one lane-group scan,
-// {cdf, t0} pairs in shared memory, branch-free binary search per fine edge, reciprocal-based divisions,
-// one lg2 per KL term.  The backward keeps every edge's (cell, F, x) from its forward phase in shared
-// memory instead of searching and evaluating erf twice, and walks the edges in per-lane consecutive runs
-// so that the scatter into a coarse cell is accumulated in registers and flushed once per (lane, cell) --
-// shared-memory float atomics are CAS loops on this architecture, and peaked fine histograms put whole
-// runs of edges into one cell.  Round-1 profile of the generic kernels above: profiles/r01_ncu_dp_loss_*.md.
+// Fast path (S0 <= 256): G lanes per ray, C coarse cells per lane (G*C >= S0, a power of two), K fine-side
+// chunks per lane (S1 + 1 <= K*G).
+//   * every global load of the ray is requested before the first dependent instruction;
+//   * each coarse cell becomes one 32-byte shared-memory record {t0, cdf, a, b | lt, 1/pin, p0, 1/sigma} with
+//     a = t0 + mu*width and b = 1/(sigma*width), so a fine edge costs one search, two 16-byte shared loads,
+//     x = (t-a)*b, one erf and two FMAs -- the divisions are per cell, not per edge, and nothing is gathered
+//     from global memory inside the edge loop (a gather there puts a DRAM latency into every chunk);
+//   * the coarse CDF is a per-lane serial sum plus ONE lane-group scan in double (monotone, ties exact);
+//   * the K interval searches of a lane run in lock step (common.cuh: SmemSearch);
+//   * one lg2 per KL term:  sum_k p1 (log p1 - log qn) = (1/Z1) sum_k pe ln(pe/qe) + ln(Zq/Z1);
+//   * backward: every edge's (cell, F, x) stays in registers from the forward phase; the scatter into the
+//     coarse cells is a plain read-modify-write when all edges of a chunk fall into different cells (checked
+//     with match.any) and shared-memory atomics otherwise (float atomics on shared memory are CAS loops).
+// Round-1 profile of the generic kernels above: profiles/r01_ncu_dp_loss_*.md.
 // ------------------------------------------------------------------------------------------
 constexpr float INF_F = __builtin_huge_valf();
-// division that keeps IEEE semantics for a zero divisor (degenerate cells), fast otherwise
-__device__ __forceinline__ float div_guard(float a, float b) { return b != 0.f ? div_fast(a, b) : a / b; }
 
-// K: fine-side chunks per lane (S1 + 1 <= K*G); all of a ray's global loads are requested up front.
+// 1/x with one Newton step on the SFU reciprocal (correctly rounded except in rare cases); IEEE for x = 0
+__device__ __forceinline__ float rcp_nr(float x) {
+    if (x == 0.f) return 1.0f / x;
+    float r = rcp_(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+
+// Standard normal CDF through erfc(z) = t exp(-z^2 + P(t)), t = 1/(1 + z/2) (Chebyshev fit, fractional error
+// < 1.2e-7 for every z >= 0, Numerical Recipes 6.2): 10 FMAs and two SFU operations instead of the ~45
+// instructions of erff, and -- unlike 0.5(1 + erf) -- it keeps its RELATIVE accuracy in the lower tail.
+__device__ __forceinline__ float normal_cdf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678f;
+    const float t = rcp_(fmaf(0.5f, z, 1.0f));
+    float p = fmaf(t, 0.17087277f, -0.82215223f);
+    p = fmaf(t, p, 1.48851587f); p = fmaf(t, p, -1.13520398f); p = fmaf(t, p, 0.27886807f);
+    p = fmaf(t, p, -0.18628806f); p = fmaf(t, p, 0.09678418f); p = fmaf(t, p, 0.37409196f);
+    p = fmaf(t, p, 1.00002368f); p = fmaf(t, p, -1.26551223f);
+    const float half_erfc = 0.5f * t * ex2_(fmaf(-z, z, p) * L2E);
+    return x <= 0.f ? half_erfc : 1.0f - half_erfc;      // NaN falls through to 1 - NaN = NaN
+}
+
+__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }     // stride-C writes of the blocked lanes: no bank conflicts
+
 template <int G, int C, int K, bool BWD>
-struct FastDp {
+struct CellDp {
     static constexpr int P = G * C;
-    // floats per ray
-    static __host__ __device__ int floats(int S1) {
-        int e = S1 + 2;                                   // E[S1+1] (+1 pad)
-        int f = 2 * (P + 1) + P + e;                      // cb, p0, E
-        if (BWD) f += (P + 1) + (P + 1) + 3 * P + 3 * e;  // cum, gcdf, gp0/gmu/gsg, edge j/F/x
-        return (f + 1) & ~1;                              // keep float2 alignment
+    static constexpr int NSK = ((P + (P >> 5) + 2) + 3) & ~3;            // skewed array length (multiple of 4)
+    static __host__ __device__ constexpr int e_floats(int S1) { return (S1 + 2 + 3) & ~3; }
+    static __host__ __device__ constexpr int floats(int S1) {
+        return 4 * (P + 1) + P + 2 * NSK + e_floats(S1) + (BWD ? P + 4 * P : 0);
     }
-    float2* cb; float *p0, *E, *cum, *gcdf, *gp0, *gmu, *gsg, *eF, *ex; int* ej;
-    __device__ FastDp(float* base, int S1) {
-        const int e = S1 + 2;
-        cb = reinterpret_cast<float2*>(base); p0 = base + 2 * (P + 1); E = p0 + P;
-        if (BWD) {
-            cum = E + e; gcdf = cum + (P + 1); gp0 = gcdf + (P + 1); gmu = gp0 + P; gsg = gmu + P;
-            ej = reinterpret_cast<int*>(gsg + P); eF = gsg + P + e; ex = eF + e;
-        }
+    float4* rec;     // [P+1] {t0, a, b, lt}: search key first; a = t0 + mu*width, b = 1/(sigma*width)
+    float* ipin;     // [P]   1/part_inside
+    float* cdf;      // [NSK] skewed: coarse CDF at the cell's left edge
+    float* p0;       // [NSK] skewed: normalised coarse pdf
+    float* E;        // [S1+2] clamped CDF estimates at the fine edges
+    float* isig;     // [P]   1/sigma                              (backward only)
+    float* acc;      // [4][P] sum gE, gE F, gE phi, gE phi x     (backward only)
+    __device__ CellDp(float* base, int S1) {
+        rec = reinterpret_cast<float4*>(base);
+        ipin = base + 4 * (P + 1);
+        cdf = ipin + P; p0 = cdf + NSK; E = p0 + NSK;
+        isig = E + e_floats(S1); acc = isig + P;
     }
+    // per-lane state of the fine side
+    struct Fine { float w1[K]; int j[K]; float F[K], x[K]; };   // j < 0: estimate clamped to 1 (no gradient)
+    float tie[C];                                                // d min(1,cum_m)/d cum_m for the lane's m = e0+c+1
 
-    // normalised coarse pdf, CDF, clamped edge estimates E_k, the three normalisers
-    __device__ __forceinline__ RayState forward(const DpArgs& a, int64_t ray, int gl, float (&w1v)[K]) {
+    __device__ __forceinline__ RayState forward(const DpArgs& a, int64_t ray, int gl, Fine& fs) {
         RayState rs;
         const int S0 = a.S0, S1 = a.S1;
-        const float* w0r = a.w0 + ray * S0;
         const float* t1r = a.t1 + ray * (S1 + 1);
         const float* w1r = a.w1 + ray * S1;
+        const float* t0r = a.t0 + ray * (S0 + 1);
+        const int64_t r0 = ray * S0;
         const int e0 = gl * C;
+        // ---- all global loads ----
         float t1v[K];
 #pragma unroll
         for (int c = 0; c < K; ++c) {
             const int k = c * G + gl;
             t1v[c] = k <= S1 ? __ldg(t1r + k) : 0.f;
-            w1v[c] = k < S1 ? __ldg(w1r + k) : 0.f;
+            fs.w1[c] = k < S1 ? __ldg(w1r + k) : 0.f;
         }
-        float v[C], part = 0.f;
+        float w0v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w0v[c] = __ldg(a.w0 + r0 + min(e0 + c, S0 - 1));       // blocked: lane owns e0..e0+C-1
+        float t0v[C + 1], t0n[C], muv[C], sgv[C], ltv[C], piv[C];                            // interleaved: q = gl + c*G
+#pragma unroll
+        for (int c = 0; c <= C; ++c) { const int q = gl + c * G; t0v[c] = q <= S0 ? __ldg(t0r + q) : INF_F; }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float w = __ldg(w0r + min(e0 + c, S0 - 1));
-            v[c] = e0 + c < S0 ? w + EPS : 0.f;
-            part += v[c];
+            const int q = min(gl + c * G, S0 - 1);
+            t0n[c] = __ldg(t0r + q + 1);
+            muv[c] = __ldg(a.mus0 + r0 + q); sgv[c] = __ldg(a.sig0 + r0 + q);
+            ltv[c] = __ldg(a.lt0 + r0 + q); piv[c] = __ldg(a.pin0 + r0 + q);
         }
-        const float* t0r = a.t0 + ray * (S0 + 1);
-        for (int q = gl; q <= P; q += G) {
-            cb[q].y = q <= S0 ? __ldg(t0r + q) : INF_F;
-            if (q > S0) cb[q].x = 2.f;
-        }
+        // ---- fine-side normalisers ----
         float p1 = 0.f, raw1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < K; ++c) if (c * G + gl < S1) { raw1 += w1v[c]; p1 += w1v[c] + EPS; }
+        for (int c = 0; c < K; ++c) if (c * G + gl < S1) { raw1 += fs.w1[c]; p1 += fs.w1[c] + EPS; }
+        // ---- coarse pdf and CDF (blocked) ----
+        float v[C], part = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { v[c] = e0 + c < S0 ? w0v[c] + EPS : 0.f; part += v[c]; }
         rs.Z0 = group_sum<G>(part);
         rs.Z1 = group_sum<G>(p1);
         rs.relevant = !a.blender || group_sum<G>(raw1) > 1e-10f;      // dd_utils.py:16
         double incl[C], run = 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float pc = div_fast(v[c], rs.Z0);
-            if (e0 + c < S0) p0[e0 + c] = pc;
+            const float pc = div_fast(v[c], rs.Z0);
+            p0[skew(e0 + c)] = pc;
             run += (double)pc; incl[c] = run;
         }
-        double lanes_incl = group_incl_sum_d<G>(run, gl);
+        const double lanes_incl = group_incl_sum_d<G>(run, gl);
         double off = __shfl_up_sync(FULL, lanes_incl, 1, G);
         if (gl == 0) off = 0.0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {                     // cdf[m] = min(1, sum_{i<m} p0_i), m = 1..S0-1
             const int m = e0 + c + 1;
+            tie[c] = 0.f;
             if (m <= S0 - 1) {
-                float cu = (float)(off + incl[c]);
-                cb[m].x = fminf(1.0f, cu);
-                if (BWD) cum[m] = cu;
+                const float cu = (float)(off + incl[c]);
+                cdf[skew(m)] = fminf(1.0f, cu);
+                tie[c] = cu < 1.0f ? 1.0f : (cu == 1.0f ? 0.5f : 0.f);   // torch.minimum's tie rule
             }
         }
-        if (gl == 0) { cb[0].x = 0.f; cb[S0].x = 1.f; if (BWD) { cum[0] = 0.f; cum[S0] = 2.f; } }
+        if (gl == 0) cdf[0] = 0.f;
+        // ---- per-cell constants (interleaved) ----
+#pragma unroll
+        for (int c = 0; c <= C; ++c) {
+            const int q = gl + c * G;
+            if (q <= P) {
+                float4 r = make_float4(t0v[c], 0.f, 0.f, 0.f);
+                if (c < C && q < S0) {
+                    const float width = t0n[c] - t0v[c];
+                    r.y = t0v[c] + muv[c] * width;                    // a: the Gaussian's mean in ray space
+                    r.z = rcp_nr(sgv[c] * width);                     // b: 1 / its standard deviation
+                    r.w = ltv[c];
+                    ipin[q] = rcp_nr(piv[c]);
+                    if (BWD) isig[q] = rcp_nr(sgv[c]);
+                }
+                rec[q] = r;
+            }
+        }
         __syncwarp();
-        const float* mur = a.mus0 + ray * S0; const float* sgr = a.sig0 + ray * S0;
-        const float* ltr = a.lt0 + ray * S0; const float* pir = a.pin0 + ray * S0;
+        // ---- fine edges: coarse cell by binary search (dd_utils.py:43, strict), estimated CDF ----
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(rec);
+        unsigned at[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) at[c] = sbase;
+        SmemSearch<P / 2, true, K, 16>::run(at, t1v);
 #pragma unroll
         for (int c = 0; c < K; ++c) {
             const int k = c * G + gl;
-            if (k > S1) break;
-            const float t = t1v[c];
-            int pos = 0;                                  // #{q in 1..P-1 : t0[q] < t}  (dd_utils.py:43, strict)
-#pragma unroll
-            for (int step = P / 2; step >= 1; step /= 2)
-                if (cb[pos + step].y < t) pos += step;
-            int j = min(pos, S0 - 1);
-            while (j > 0 && cb[j - 1].x == cb[j].x) --j;  // torch.max: first index of the maximum
-            const float2 a0 = cb[j];
-            const float width = cb[j + 1].y - a0.y;
-            const float mr = a0.y + __ldg(mur + j) * width;
-            const float sr = __ldg(sgr + j) * width;
-            const float pin = __ldg(pir + j);
-            const float x = div_guard(t - mr, sr);
-            const float num = normal_cdff_(x) - __ldg(ltr + j);
-            const float F = div_guard(num, pin);
-            const float eraw = a0.x + F * p0[j];
+            if (k > S1) { fs.j[c] = -1; fs.F[c] = 0.f; fs.x[c] = 0.f; continue; }
+            int j = min((int)((at[c] - sbase) >> 4), S0 - 1);
+            const float cj = cdf[skew(j)];
+            while (j > 0 && cdf[skew(j - 1)] == cj) --j;   // torch.max: first index of the maximum
+            const float4 r = rec[j];
+            const float x = (t1v[c] - r.y) * r.z;
+            const float F = (normal_cdf_fast(x) - r.w) * ipin[j];
+            const float eraw = cj + F * p0[skew(j)];
             E[k] = eraw > 1.0f ? 1.0f : eraw;             // dd_utils.py:66
-            if (BWD) { ej[k] = eraw > 1.0f ? -1 - j : j; eF[k] = F; ex[k] = x; }
+            fs.j[c] = eraw > 1.0f ? -1 : j; fs.F[c] = F; fs.x[c] = x;
         }
         __syncwarp();
         float zq = 0.f;
-        for (int k = gl; k < S1; k += G) { float q = E[k + 1] - E[k]; zq += (q < 0.f ? 0.f : q) + EPS; }
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            const int k = c * G + gl;
+            if (k < S1) { float q = E[k + 1] - E[k]; zq += (q < 0.f ? 0.f : q) + EPS; }
+        }
         rs.Zq = group_sum<G>(zq);
         return rs;
     }
 };
 
+// Forward: one KL value and one relevance flag per ray into scratch[4 + ray], scratch[4 + N + ray]; the mean
+// is taken by dp_loss_finish_kernel in a fixed order (bit-reproducible, no same-address atomics).
 template <int G, int C, int K>
-__global__ void __launch_bounds__(256) dp_loss_fwd_fast_kernel(DpArgs a, float* __restrict__ loss_out,
-                                                                float* __restrict__ scratch, int per_ray) {
-    extern __shared__ __align__(8) float smem[];
-    __shared__ float blk[2];
+__global__ void __launch_bounds__(128) dp_loss_fwd_fast_kernel(DpArgs a, float* __restrict__ scratch, int per_ray) {
+    extern __shared__ __align__(16) float smem[];
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     int64_t ray = (int64_t)blockIdx.x * (blockDim.x / G) + grp;
     const bool valid = ray < a.N;
     if (!valid) ray = a.N - 1;
-    if (threadIdx.x < 2) blk[threadIdx.x] = 0.f;
-    __syncthreads();
-    FastDp<G, C, K, false> sm(smem + (size_t)grp * per_ray, a.S1);
-    float w1v[K];
-    RayState rs = sm.forward(a, ray, gl, w1v);
-    // sum_k p1 (log p1 - log qn) = (1/Z1) sum_k pe ln(pe/qe) + ln(Zq/Z1),  pe = w1+eps, qe = max(q,0)+eps
+    using D = CellDp<G, C, K, false>;
+    D sm(smem + (size_t)grp * per_ray, a.S1);
+    typename D::Fine fs;
+    RayState rs = sm.forward(a, ray, gl, fs);
     float l = 0.f;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
@@ -349,24 +402,29 @@ __global__ void __launch_bounds__(256) dp_loss_fwd_fast_kernel(DpArgs a, float* 
         if (k >= a.S1) break;
         float q = sm.E[k + 1] - sm.E[k];
         float qe = (q < 0.f ? 0.f : q) + EPS;
-        float pe = w1v[c] + EPS;
+        float pe = fs.w1[c] + EPS;
         l += pe * lg2_(pe * rcp_(qe));
     }
     l = group_sum<G>(l);
-    if (gl == 0 && valid && rs.relevant) {
-        float kl = l * LN2 / rs.Z1 + logf(rs.Zq / rs.Z1);
-        atomicAdd(&blk[0], kl); atomicAdd(&blk[1], 1.0f);
+    if (gl == 0 && valid) {
+        scratch[4 + ray] = rs.relevant ? l * LN2 / rs.Z1 + logf(rs.Zq / rs.Z1) : 0.f;
+        scratch[4 + a.N + ray] = rs.relevant ? 1.f : 0.f;
     }
+}
+
+__global__ void __launch_bounds__(1024) dp_loss_finish_kernel(float* __restrict__ scratch, float* __restrict__ loss_out,
+                                                               int64_t N, int S1) {
+    __shared__ float ssum[32], scnt[32];
+    float sum = 0.f, cnt = 0.f;
+    for (int64_t i = threadIdx.x; i < N; i += 1024) { sum += scratch[4 + i]; cnt += scratch[4 + N + i]; }
+    sum = group_sum<32>(sum); cnt = group_sum<32>(cnt);
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; scnt[threadIdx.x >> 5] = cnt; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(scratch + 0, blk[0]);
-        atomicAdd(scratch + 1, blk[1]);
-        __threadfence();
-        unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(scratch) + 2, 1u);
-        if (ticket == gridDim.x - 1) {
-            __threadfence();
-            float sum = atomicAdd(scratch + 0, 0.f), cnt = atomicAdd(scratch + 1, 0.f);
-            *loss_out = cnt > 0.f ? sum / (cnt * (float)a.S1) : 0.f;   // reduction='mean' over kept rays x S1
+    if (threadIdx.x < 32) {
+        sum = group_sum<32>(ssum[threadIdx.x]); cnt = group_sum<32>(scnt[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            scratch[0] = sum; scratch[1] = cnt;
+            *loss_out = cnt > 0.f ? sum / (cnt * (float)S1) : 0.f;     // reduction='mean' over kept rays x S1
         }
     }
 }
@@ -376,93 +434,86 @@ __global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, const f
                                                                 const float* __restrict__ scratch,
                                                                 float* __restrict__ g_w0, float* __restrict__ g_mus0,
                                                                 float* __restrict__ g_sig0, int per_ray) {
-    extern __shared__ __align__(8) float smem[];
+    extern __shared__ __align__(16) float smem[];
     constexpr int P = G * C;
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     int64_t ray = (int64_t)blockIdx.x * (blockDim.x / G) + grp;
     const bool valid = ray < a.N;
     if (!valid) ray = a.N - 1;
     const int S0 = a.S0, S1 = a.S1;
-    FastDp<G, C, K, true> sm(smem + (size_t)grp * per_ray, S1);
-    float w1v[K];
-    RayState rs = sm.forward(a, ray, gl, w1v);
+    using D = CellDp<G, C, K, true>;
+    D sm(smem + (size_t)grp * per_ray, S1);
+    typename D::Fine fs;
+    for (int i = gl; i < 4 * P; i += G) sm.acc[i] = 0.f;  // [4][P]: sum gE, gE F, gE phi, gE phi x per coarse cell
+    RayState rs = sm.forward(a, ray, gl, fs);             // (its __syncwarp()s order the zero fill)
     const float cnt = __ldg(scratch + 1);
     const bool live = rs.relevant && cnt > 0.f;           // uniform over the lane group
     const float scale = live ? __ldg(g_loss) / (cnt * (float)S1) : 0.f;
-    for (int i = gl; i <= P; i += G) { sm.gcdf[i] = 0.f; if (i < P) { sm.gp0[i] = 0.f; sm.gmu[i] = 0.f; sm.gsg[i] = 0.f; } }
-    __syncwarp();
     const float zr = rs.Zq / rs.Z1, sz = scale / rs.Zq;
-    const float* w1r = a.w1 + ray * S1;
-    auto gq = [&](int k) -> float {                       // dL/dq_k, zero where the clamp q<0 -> 0 is active
-        float q = sm.E[k + 1] - sm.E[k];
-        if (q < 0.f) return 0.f;
-        float pe = __ldg(w1r + k) + EPS;
-        return sz * (1.0f - pe * rcp_(q + EPS) * zr);     // scale/Zq (1 - p1/qn)
-    };
-    // every lane walks KC consecutive edges; contributions to one coarse cell accumulate in registers
-    const int KC = (S1 + 1 + G - 1) / G;
-    const float* pir = a.pin0 + ray * S0;
-    int cur = -1;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    auto flush = [&]() {
-        if (cur >= 0) {
-            if (acc0 != 0.f) atomicAdd(sm.gcdf + cur, acc0);
-            if (acc1 != 0.f) atomicAdd(sm.gp0 + cur, acc1);
-            if (acc2 != 0.f) atomicAdd(sm.gmu + cur, acc2);
-            if (acc3 != 0.f) atomicAdd(sm.gsg + cur, acc3);
+    const int lane = threadIdx.x & 31;
+    float carry = 0.f;                                    // gq of the previous chunk's last edge
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const int k = c * G + gl;
+        if (c * G > S1) break;                            // uniform
+        // dL/dq_k = scale/Zq (1 - p1/qn), zero where the clamp q<0 -> 0 is active
+        float gqk = 0.f;
+        if (k < S1) {
+            const float q = sm.E[k + 1] - sm.E[k];
+            if (!(q < 0.f)) gqk = sz * (1.0f - (fs.w1[c] + EPS) * rcp_(q + EPS) * zr);
         }
-    };
-    if (live) {
-        for (int c = 0; c < KC; ++c) {
-            const int k = gl * KC + c;
-            if (k > S1) break;
-            const int jj = sm.ej[k];
-            if (jj < 0) continue;                         // clamp est_cdf > 1 -> 1 blocks the gradient
-            const float gE = (k >= 1 ? gq(k - 1) : 0.f) - (k <= S1 - 1 ? gq(k) : 0.f);
-            if (gE == 0.f) continue;
-            if (jj != cur) { flush(); cur = jj; acc0 = acc1 = acc2 = acc3 = 0.f; }
-            const float F = sm.eF[k], x = sm.ex[k];
-            const float2 a0 = sm.cb[jj];
-            const float width = sm.cb[jj + 1].y - a0.y;
-            const float sr = __ldg(a.sig0 + ray * S0 + jj) * width;
-            const float pin = __ldg(pir + jj);
-            const float gx = div_guard(gE * sm.p0[jj], pin) * (0.3989422804f * ex2_(-0.5f * x * x * L2E));
-            const float gxs = div_guard(gx, sr) * width;
-            acc0 += gE; acc1 += gE * F; acc2 -= gxs; acc3 -= gxs * x;
+        float gprev = __shfl_up_sync(FULL, gqk, 1, G);
+        if (gl == 0) gprev = carry;
+        carry = __shfl_sync(FULL, gqk, G - 1, G);
+        const float gE = gprev - gqk;                     // E_k enters q_{k-1} with +1 and q_k with -1
+        const int j = fs.j[c];
+        const bool active = live && j >= 0 && gE != 0.f;
+        const float x = fs.x[c];
+        const float v2 = gE * (0.3989422804f * ex2_(-0.5f * x * x * L2E));
+        // scatter: plain read-modify-write unless two edges of this chunk share a coarse cell
+        const int key = active ? ((lane / G) << 16 | j) : (-1 - lane);
+        const unsigned peers = __match_any_sync(FULL, key);
+        const bool conflict = __any_sync(FULL, active && peers != (1u << lane));
+        if (active) {
+            float* p = sm.acc + j;
+            if (conflict) {
+                atomicAdd(p, gE); atomicAdd(p + P, gE * fs.F[c]); atomicAdd(p + 2 * P, v2); atomicAdd(p + 3 * P, v2 * x);
+            } else {
+                p[0] += gE; p[P] += gE * fs.F[c]; p[2 * P] += v2; p[3 * P] += v2 * x;
+            }
         }
-        flush();
+        __syncwarp();
     }
-    __syncwarp();
-    // cdf[m] = min(1, cum[m]): route g_cdf[m] to p0[0..m-1] for m = 1..S0-1 (suffix sum), with
-    // torch.minimum's tie rule (half the gradient when cum == 1).  Lane owns cells e0..e0+C-1.
+    // cdf[m] = min(1, cum[m]): route g_cdf[m] to p0[0..m-1] for m = 1..S0-1 (suffix sum).  Lane owns cells e0..e0+C-1.
     const int e0 = gl * C;
     float h[C], tail = 0.f;
 #pragma unroll
     for (int c = C - 1; c >= 0; --c) {                    // h[c] = sum over m in (e0+c, e0+C] of routed g_cdf[m]
         const int m = e0 + c + 1;
-        float r = 0.f;
-        if (m <= S0 - 1) { float cu = sm.cum[m]; r = sm.gcdf[m] * (cu < 1.0f ? 1.0f : (cu == 1.0f ? 0.5f : 0.f)); }
-        tail += r;
+        if (m <= S0 - 1) tail += sm.acc[m] * sm.tie[c];
         h[c] = tail;
     }
     const float suf_incl = group_suffix_sum<G>(tail, gl);
     const float after = suf_incl - tail;                  // routed g_cdf of all later lanes
-    float gp[C], dot = 0.f;
+    float gp[C], pc[C], dot = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int i = e0 + c;
-        gp[c] = i < S0 ? sm.gp0[i] + h[c] + after : 0.f;
-        dot += i < S0 ? gp[c] * sm.p0[i] : 0.f;
+        pc[c] = sm.p0[skew(i)];
+        gp[c] = i < S0 ? sm.acc[P + i] + h[c] + after : 0.f;
+        dot += i < S0 ? gp[c] * pc[c] : 0.f;
     }
     dot = group_sum<G>(dot);
     if (valid) {
+        const float iz0 = 1.0f / rs.Z0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int i = e0 + c;
             if (i < S0) {
-                g_w0[ray * S0 + i] = live ? (gp[c] - dot) / rs.Z0 : 0.f;   // p0 = (w0+eps)/sum(w0+eps)
-                g_mus0[ray * S0 + i] = sm.gmu[i];
-                g_sig0[ray * S0 + i] = sm.gsg[i];
+                const float kc = -pc[c] * sm.ipin[i] * sm.isig[i];        // d x / d mu, d x / d sigma carry -p0/(pin sigma)
+                g_w0[ray * S0 + i] = live ? (gp[c] - dot) * iz0 : 0.f;    // p0 = (w0+eps)/sum(w0+eps)
+                g_mus0[ray * S0 + i] = live ? kc * sm.acc[2 * P + i] : 0.f;
+                g_sig0[ray * S0 + i] = live ? kc * sm.acc[3 * P + i] : 0.f;
             }
         }
     }
@@ -505,12 +556,14 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float
     DpArgs a{t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, N, S0, S1};
     bool fast = dispatch_fast(S0, S1, [&](auto g, auto c, auto kk) {
         constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
-        const int per_ray = FastDp<G, C, K, false>::floats(S1);
-        const size_t bytes = (size_t)(256 / G) * per_ray * sizeof(float);
+        const int per_ray = CellDp<G, C, K, false>::floats(S1);
+        const size_t bytes = (size_t)(128 / G) * per_ray * sizeof(float);
         if (bytes > 200 * 1024) return false;
         auto kern = dp_loss_fwd_fast_kernel<G, C, K>;
         if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        kern<<<ceil_div(N, 256 / G), 256, bytes, st>>>(a, loss_out, scratch, per_ray);
+        kern<<<ceil_div(N, 128 / G), 128, bytes, st>>>(a, scratch, per_ray);
+        dp_loss_finish_kernel<<<1, 1024, 0, st>>>(scratch, loss_out, N, S1);
+        ddnerf::count_launches(1);
         return true;
     });
     if (!fast) {
@@ -536,7 +589,7 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bool fast = dispatch_fast(S0, S1, [&](auto g, auto c, auto kk) {
         constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
-        const int per_ray = FastDp<G, C, K, true>::floats(S1);
+        const int per_ray = CellDp<G, C, K, true>::floats(S1);
         const size_t bytes = (size_t)(128 / G) * per_ray * sizeof(float);
         if (bytes > 200 * 1024) return false;
         auto kern = dp_loss_bwd_fast_kernel<G, C, K>;

@@ -187,9 +187,16 @@ struct FastCdf {
         const int e0 = gl * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) w[c] = __ldg(w_row + min(e0 + c, S - 1));
-        for (int q = gl; q <= P; q += G) {
-            cb[q].y = q <= S ? __ldg(bins_row + q) : 0.f;
-            if (q > S) cb[q].x = __int_as_float(0x7f800000);
+        float bv[C + 1];                                  // fence-posts q = gl + c*G, all requested before the first use
+#pragma unroll
+        for (int c = 0; c <= C; ++c) { const int q = gl + c * G; bv[c] = q <= S ? __ldg(bins_row + q) : 0.f; }
+#pragma unroll
+        for (int c = 0; c <= C; ++c) {
+            const int q = gl + c * G;
+            if (q <= P) {
+                cb[q].y = bv[c];
+                if (q > S) cb[q].x = __int_as_float(0x7f800000);
+            }
         }
         float prev = __shfl_up_sync(FULL, w[C - 1], 1, G);
         float next = __shfl_down_sync(FULL, w[0], 1, G);
@@ -220,23 +227,29 @@ struct FastCdf {
         if (gl == 0) { cb[0].x = 0.f; cb[S].x = 1.f; }
         __syncwarp();
     }
-    // j = #{m in [0,S] : cdf[m] <= u} - 1  (u >= 0)
-    __device__ static __forceinline__ int search(const float2* cb, int S, float u) {
-        int pos = 0;
+    // j[m] = #{q in [0,S] : cdf[q] <= u[m]} - 1  (u >= 0), M searches in lock step (common.cuh: SmemSearch)
+    template <int M>
+    __device__ static __forceinline__ void search(const float2* cb, int S, const float (&u)[M], int (&j)[M]) {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(cb);
+        unsigned at[M];
 #pragma unroll
-        for (int step = P / 2; step >= 1; step /= 2)
-            if (cb[pos + step].x <= u) pos += step;
-        if (S == P && u >= 1.0f) pos = S;                 // position P (= S) is outside the searched range
-        return pos;
+        for (int m = 0; m < M; ++m) at[m] = base;
+        SmemSearch<P / 2, false, M, 8>::run(at, u);
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            j[m] = (int)((at[m] - base) >> 3);
+            if (S == P && u[m] >= 1.0f) j[m] = S;         // position P (= S) is outside the searched range
+        }
     }
 };
 
 struct UGen {
-    float det_step; USpec us; int n;
-    __device__ UGen(const USpec& u, int n_) : us(u), n(n_) { det_step = us.hi / (float)(n - 1); }
+    float det_step, rdiv; USpec us; int n;
+    __device__ UGen(const USpec& u, int n_) : us(u), n(n_) { det_step = us.hi / (float)(n - 1); rdiv = rcp_(us.div); }
     __device__ __forceinline__ float operator()(int k, float rnd) const {
         if (us.det) return k < n / 2 ? det_step * (float)k : us.hi - det_step * (float)(n - k - 1);
-        float u = (float)k * us.stride + div_fast(rnd, us.div);
+        const float q = rnd * rdiv;                       // rnd / div, reciprocal + residual correction (div_fast)
+        float u = (float)k * us.stride + fmaf(fmaf(-q, us.div, rnd), rdiv, q);
         u = fminf(u, 0.9999f);
         if (us.clamp0) u = fmaxf(u, 0.0f);
         return u;
@@ -265,20 +278,29 @@ __global__ void __launch_bounds__(256) sample_pdf_fast_kernel(const float* __res
     if (!valid) return;
     const UGen ugen(us, n);
     float* orow = out + ray * n;
+    float u[K];
+    int j[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) u[c] = ugen(c * G + gl, rnd[c]);
+    F::search(cb, S, u, j);                                              // all K interval searches in lock step
 #pragma unroll
     for (int c = 0; c < K; ++c) {
         const int k = c * G + gl;
         if (k >= n) break;
-        const float u = ugen(k, rnd[c]);
-        const int j = F::search(cb, S, u);
-        const float2 a0 = cb[j], a1 = cb[min(j + 1, S)];
-        float t = div_fast(u - a0.x, a1.x - a0.x);
+        const float2 a0 = cb[j[c]], a1 = cb[min(j[c] + 1, S)];
+        float t = div_fast(u[c] - a0.x, a1.x - a0.x);
         if (t != t) t = 0.f;                                             // nan_to_num(., 0)
         t = fminf(fmaxf(t, 0.f), 1.f);
         orow[k] = a0.y + t * (a1.y - a0.y);
-        if (idx_out) idx_out[ray * n + k] = j;
+        if (idx_out) idx_out[ray * n + k] = j[c];
     }
 }
+
+// DDNeRF variant.  The per-cell Gaussian parameters (part_inside, left_tail, sigma, mu) are staged in shared
+// memory next to the {cdf, bin} pairs -- gathered from global memory they put one DRAM latency into every
+// output chunk.  Dynamic shared memory per ray: P float4 + (P+1) float2 (rounded to 16 bytes).
+template <int G, int C>
+__host__ __device__ constexpr int dd_ray_smem_bytes() { return G * C * 16 + ((G * C + 1) * 8 + 15) / 16 * 16; }
 
 template <int G, int C, int K>
 __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
@@ -287,22 +309,44 @@ __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
     const float* __restrict__ rand, float* __restrict__ out, int32_t* __restrict__ idx_out, int64_t N, int S, int n,
     int pdf_padding, float near_cfg, float far_cfg, USpec us) {
     using F = FastCdf<G, C>;
-    __shared__ float2 cbs[256 / G][F::P + 1];
+    extern __shared__ float4 dd_smem[];
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     int64_t ray = (int64_t)blockIdx.x * (256 / G) + grp;
     const bool valid = ray < N;
     if (!valid) ray = N - 1;
-    float2* cb = cbs[grp];
+    float4* pr = dd_smem + (size_t)grp * (dd_ray_smem_bytes<G, C>() / 16);    // {pin, lt, sigma, mu} per cell
+    float2* cb = reinterpret_cast<float2*>(pr + F::P);
     float rnd[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) rnd[c] = (rand && c * G + gl < n) ? __ldg(rand + ray * n + c * G + gl) : 0.f;
-    F::build(weights + ray * S, bins + ray * (S + 1), cb, S, gl, pdf_padding);
-    const float* mu_r = mus + ray * S;
-    const float* sg_r = sigmas + ray * S;
-    const float* pin_r = part_inside + ray * S;
-    const float* lt_r = left_tail + ray * S;
+    {
+        const float* mu_r = mus + ray * S;
+        const float* sg_r = sigmas + ray * S;
+        const float* pin_r = part_inside + ray * S;
+        const float* lt_r = left_tail + ray * S;
+        float4 pv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int q = min(gl + c * G, S - 1);
+            pv[c] = make_float4(__ldg(pin_r + q), __ldg(lt_r + q), __ldg(sg_r + q), __ldg(mu_r + q));
+        }
+        F::build(weights + ray * S, bins + ray * (S + 1), cb, S, gl, pdf_padding);   // ends with __syncwarp
+#pragma unroll
+        for (int c = 0; c < C; ++c) pr[gl + c * G] = pv[c];
+        __syncwarp();
+    }
     const UGen ugen(us, n);
     float* orow = out + ray * n;
+    float u[K];
+    int j[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) u[c] = ugen(c * G + gl, rnd[c]);
+    if (S == 1) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) j[c] = 0;
+    } else {
+        F::search(cb, S, u, j);
+    }
     bool ok = true;
     float prev_last = -__int_as_float(0x7f800000);
 #pragma unroll
@@ -312,24 +356,23 @@ __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
         const bool in = k < n;
         float val = __int_as_float(0x7f800000);
         if (in) {
-            const float u = ugen(k, rnd[c]);
             float z, b0, b1;
             int ind;
             if (S == 1) {                                                // samplers.py:185-190
                 ind = 0; b0 = cb[0].y; b1 = cb[1].y;
-                z = u * __ldg(pin_r) + __ldg(lt_r);
+                z = u[c] * pr[0].x + pr[0].y;
             } else {
-                const int j = F::search(cb, S, u);
-                const float2 a0 = cb[j], a1 = cb[min(j + 1, S)];
+                const float2 a0 = cb[j[c]], a1 = cb[min(j[c] + 1, S)];
                 b0 = a0.y; b1 = a1.y;
-                ind = j;                                                 // torch.max: first index of the maximum
+                ind = j[c];                                              // torch.max: first index of the maximum
                 while (ind > 0 && cb[ind - 1].y == cb[ind].y) --ind;
                 ind = min(ind, S - 1);
-                z = div_fast(u - a0.x, a1.x - a0.x) * __ldg(pin_r + ind) + __ldg(lt_r + ind);
+                z = div_fast(u[c] - a0.x, a1.x - a0.x) * pr[ind].x + pr[ind].y;
                 z = fminf(z, 0.999f);
             }
+            const float4 pp = pr[ind];
             z = 1.41421354f * erfinvf(2.0f * z - 1.0f);                  // math_utils.py:202-208
-            float t = fminf(fmaxf(z * __ldg(sg_r + ind) + __ldg(mu_r + ind), 0.f), 0.99999f);
+            float t = fminf(fmaxf(z * pp.z + pp.w, 0.f), 0.99999f);
             val = b0 + t * (b1 - b0);
             if (k == 0) val = near_cfg;                                  // samplers.py:210-211
             if (k == n - 1) val = far_cfg;
@@ -347,7 +390,7 @@ __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
     }
     // any lane of the group saw an inversion -> lane 0 of the group insertion-sorts the row in place
     unsigned bad = __ballot_sync(FULL, !ok);
-    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << ((threadIdx.x & 31) / G * G);
     if ((bad & gmask) && valid) {
         __syncwarp(gmask);
         if (gl == 0) {
@@ -550,9 +593,11 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bool fast = dispatch_fast(S, n, [&](auto g, auto c, auto kk) {
         constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
-        sample_pdf_mu_sigma_fast_kernel<G, C, K><<<ceil_div(N, 256 / G), 256, 0, st>>>(
-            bins, weights, mus, sigmas, part_inside, left_tail, rand, out, idx_out, N, S, n, pdf_padding, near_cfg, far_cfg,
-            us);
+        auto kern = sample_pdf_mu_sigma_fast_kernel<G, C, K>;
+        constexpr int bytes = (256 / G) * dd_ray_smem_bytes<G, C>();
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        kern<<<ceil_div(N, 256 / G), 256, bytes, st>>>(bins, weights, mus, sigmas, part_inside, left_tail, rand, out,
+                                                       idx_out, N, S, n, pdf_padding, near_cfg, far_cfg, us);
     });
     if (!fast) {
         int np2 = next_pow2(n);

@@ -271,7 +271,7 @@ class _DpLoss(torch.autograd.Function):
         mus0, sig0, lt0, pin0 = _req(mus0, "mus_0"), _req(sig0, "sigmas_0"), _req(lt0, "left_tails_0"), _req(pin0, "part_inside")
         N, S0, S1 = w0.shape[0], w0.shape[1], w1.shape[1]
         loss = torch.empty((), device=w0.device, dtype=torch.float32)
-        scratch = torch.empty(4, device=w0.device, dtype=torch.float32)
+        scratch = torch.empty(4 + 2 * N, device=w0.device, dtype=torch.float32)      # header + per-ray KL and relevance
         _lib.check(lib.ddnerf_dp_loss_forward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
                                               int(bool(blender)), _p(loss), _p(scratch), N, S0, S1, _stream()), "dp_loss_forward")
         ctx.save_for_backward(t1, t0, w1, w0, mus0, sig0, lt0, pin0, scratch)

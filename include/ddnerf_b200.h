@@ -180,8 +180,10 @@ int ddnerf_composite_backward(const float* raw, int raw_stride, const float* t, 
                               float* g_raw, float* g_mus, int64_t N, int S, void* stream);
 
 /* ---- K5: depth-distribution loss (models/dd_utils.py:6-78) ------------------------------- */
-/* scratch: >= 4 floats, zeroed by the call.  loss_out: 1 float = kl_div(..., 'mean').
- * ray_aux [N,2] receives per-ray (Z0, Zq) for the backward. */
+/* scratch: >= 4 + 2*N floats of caller-owned workspace: [0] = sum of the per-ray KL values, [1] = number of
+ * rays kept by the blender row filter (dd_utils.py:12-28), [4 .. 4+N) per-ray KL, [4+N .. 4+2N) per-ray kept
+ * flag; the mean is taken over the per-ray values in a fixed order (bit-reproducible).
+ * loss_out: 1 float = kl_div(..., 'mean'). */
 int ddnerf_dp_loss_forward(const float* t1, const float* t0, const float* w1, const float* w0,
                            const float* mus0, const float* sigmas0, const float* lt0,
                            const float* pin0, int blender, float* loss_out, float* scratch,

@@ -102,7 +102,7 @@ def main():
                 _lib.check(lib.ddnerf_composite_backward(_p(raw), 4, _p(t0), _p(rd), rd.stride(0), _p(noise), 1.0, None, 0, 1,
                                                          _p(g_rgb), None, None, _p(g_w), None, None, _p(g_raw), None, N, S,
                                                          _stream()), "composite_backward")
-            dp_scratch = torch.zeros(4, device=dev)
+            dp_scratch = torch.zeros(4 + 2 * N, device=dev)
             dp_out = torch.empty((), device=dev)
             g_one = torch.ones((), device=dev)
             g_w0, g_mu, g_sg = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
