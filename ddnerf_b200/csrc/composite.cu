@@ -312,15 +312,18 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
     }
 }
 
-// (G, NCH) for S samples: eight chunks per lane wherever S allows, so that short rays share a warp.
+// (G, NCH) for S samples, measured (profiles/r01b_stage_roofline.md): four chunks per lane, short rays sharing a
+// warp; the register-heavy backward prefers eight chunks from S = 128 up (two rays per warp amortise its
+// per-ray epilogue; the forward is indifferent there).
 template <typename F>
-int dispatch_shape(int S, F&& f) {
+int dispatch_shape(int S, bool backward, F&& f) {
 #define DDNERF_CASE(G, NCH)                                                                               \
     if (S <= G * NCH) {                                                                                   \
         if (S == G * NCH) return f(std::integral_constant<int, G>{}, std::integral_constant<int, NCH>{}, std::true_type{}); \
         return f(std::integral_constant<int, G>{}, std::integral_constant<int, NCH>{}, std::false_type{});                  \
     }
-    DDNERF_CASE(4, 1) DDNERF_CASE(4, 2) DDNERF_CASE(4, 4) DDNERF_CASE(4, 8) DDNERF_CASE(8, 8) DDNERF_CASE(16, 8)
+    DDNERF_CASE(4, 1) DDNERF_CASE(4, 2) DDNERF_CASE(4, 4) DDNERF_CASE(8, 4) DDNERF_CASE(16, 4)
+    if (backward) { if (S > 64) { DDNERF_CASE(16, 8) } } else { DDNERF_CASE(32, 4) }
     DDNERF_CASE(32, 8) DDNERF_CASE(32, 16)
 #undef DDNERF_CASE
     return -1;
@@ -364,7 +367,7 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_forward(const float* raw, int raw_
     CompositeArgs a{raw, raw_stride, t, rd, rd_stride, use_noise ? noise : nullptr, use_noise ? noise_std : 0.f, mus,
                     white_background, blender, N, S};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = dispatch_shape(S, [&](auto g, auto nch, auto ex) {
+    int rc = dispatch_shape(S, false, [&](auto g, auto nch, auto ex) {
         return dispatch_layout(raw_vector_width(raw, raw_stride), mus != nullptr, [&](auto v, auto mu) {
             constexpr int G = decltype(g)::value, NCH = decltype(nch)::value, V = decltype(v)::value;
             constexpr bool MU = decltype(mu)::value, EX = decltype(ex)::value;
@@ -394,7 +397,7 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_backward(const float* raw, int raw
                     white_background, blender, N, S};
     CompositeGrads gr{g_rgb_map, g_disp, g_acc, g_weights, g_depth, g_cdisp};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = dispatch_shape(S, [&](auto g, auto nch, auto ex) {
+    int rc = dispatch_shape(S, true, [&](auto g, auto nch, auto ex) {
         return dispatch_layout(raw_vector_width(raw, raw_stride), mus != nullptr, [&](auto v, auto mu) {
             constexpr int G = decltype(g)::value, NCH = decltype(nch)::value, V = decltype(v)::value;
             constexpr bool MU = decltype(mu)::value, EX = decltype(ex)::value;

@@ -10,6 +10,8 @@
 // the reference forgets to filter left_tails_0 and mis-aligns it; this kernel indexes every
 // per-ray tensor consistently.  With no dropped rays (always, given the 1e-10 the compositor adds
 // to the last weight) the two agree.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -217,8 +219,8 @@ __global__ void dp_loss_bwd_kernel(DpArgs a, const float* __restrict__ g_loss, c
 //   * the K interval searches of a lane run in lock step (common.cuh: SmemSearch);
 //   * one lg2 per KL term:  sum_k p1 (log p1 - log qn) = (1/Z1) sum_k pe ln(pe/qe) + ln(Zq/Z1);
 //   * backward: every edge's (cell, F, x) stays in registers from the forward phase; the scatter into the
-//     coarse cells is a plain read-modify-write when all edges of a chunk fall into different cells (checked
-//     with match.any) and shared-memory atomics otherwise (float atomics on shared memory are CAS loops).
+//     coarse cells is a segmented lane-group scan over the (sorted) cells of a chunk's edges, so only the last
+//     lane of each run touches shared memory -- no atomics (float atomics on shared memory are CAS loops).
 // Round-1 profile of the generic kernels above: profiles/r01_ncu_dp_loss_*.md.
 // ------------------------------------------------------------------------------------------
 constexpr float INF_F = __builtin_huge_valf();
@@ -368,7 +370,7 @@ struct CellDp {
             const float F = (normal_cdf_fast(x) - r.w) * ipin[j];
             const float eraw = cj + F * p0[skew(j)];
             E[k] = eraw > 1.0f ? 1.0f : eraw;             // dd_utils.py:66
-            fs.j[c] = eraw > 1.0f ? -1 : j; fs.F[c] = F; fs.x[c] = x;
+            fs.j[c] = eraw > 1.0f ? ~j : j; fs.F[c] = F; fs.x[c] = x;
         }
         __syncwarp();
         float zq = 0.f;
@@ -450,7 +452,6 @@ __global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, const f
     const bool live = rs.relevant && cnt > 0.f;           // uniform over the lane group
     const float scale = live ? __ldg(g_loss) / (cnt * (float)S1) : 0.f;
     const float zr = rs.Zq / rs.Z1, sz = scale / rs.Zq;
-    const int lane = threadIdx.x & 31;
     float carry = 0.f;                                    // gq of the previous chunk's last edge
 #pragma unroll
     for (int c = 0; c < K; ++c) {
@@ -470,17 +471,23 @@ __global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, const f
         const bool active = live && j >= 0 && gE != 0.f;
         const float x = fs.x[c];
         const float v2 = gE * (0.3989422804f * ex2_(-0.5f * x * x * L2E));
-        // scatter: plain read-modify-write unless two edges of this chunk share a coarse cell
-        const int key = active ? ((lane / G) << 16 | j) : (-1 - lane);
-        const unsigned peers = __match_any_sync(FULL, key);
-        const bool conflict = __any_sync(FULL, active && peers != (1u << lane));
-        if (active) {
-            float* p = sm.acc + j;
-            if (conflict) {
-                atomicAdd(p, gE); atomicAdd(p + P, gE * fs.F[c]); atomicAdd(p + 2 * P, v2); atomicAdd(p + 3 * P, v2 * x);
-            } else {
-                p[0] += gE; p[P] += gE * fs.F[c]; p[2 * P] += v2; p[3 * P] += v2 * x;
-            }
+        // Scatter into the coarse cells.  The cells of consecutive edges are non-decreasing, so the edges of one
+        // cell are a run of adjacent lanes: a segmented inclusive scan (the lane d below has the same cell iff the
+        // whole stretch has) leaves each run's total in its last lane, which alone updates shared memory -- no
+        // atomics (float atomics on shared memory are CAS loops) and a fixed summation order.
+        const int jr = k > S1 ? 0x7fffffff : (j < 0 ? ~j : j);           // the edge's cell, clamped or not
+        float s0 = active ? gE : 0.f, s1 = active ? gE * fs.F[c] : 0.f, s2 = active ? v2 : 0.f, s3 = active ? v2 * x : 0.f;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const int jn = __shfl_up_sync(FULL, jr, d, G);
+            const float n0 = __shfl_up_sync(FULL, s0, d, G), n1 = __shfl_up_sync(FULL, s1, d, G);
+            const float n2 = __shfl_up_sync(FULL, s2, d, G), n3 = __shfl_up_sync(FULL, s3, d, G);
+            if (gl >= d && jn == jr) { s0 += n0; s1 += n1; s2 += n2; s3 += n3; }
+        }
+        const int jnext = __shfl_down_sync(FULL, jr, 1, G);
+        if ((gl == G - 1 || jnext != jr) && jr < S0 && (s0 != 0.f || s1 != 0.f || s2 != 0.f || s3 != 0.f)) {
+            float* p = sm.acc + jr;
+            p[0] += s0; p[P] += s1; p[2 * P] += s2; p[3 * P] += s3;
         }
         __syncwarp();
     }
@@ -527,8 +534,9 @@ bool dispatch_fast(int S0, int S1, F&& f) {
         if (S1 + 1 <= 9 * G) return f(std::integral_constant<int, G>{}, std::integral_constant<int, C>{}, std::integral_constant<int, 9>{}); \
         return false;                                                                                                      \
     }
-    // eight cells per lane wherever S allows: short rays share a warp
-    DDNERF_FAST(4, 1) DDNERF_FAST(4, 2) DDNERF_FAST(4, 4) DDNERF_FAST(4, 8) DDNERF_FAST(8, 8) DDNERF_FAST(16, 8) DDNERF_FAST(32, 8)
+    // Four cells per lane: measured faster than eight (profiles/r01b_*): these kernels are bound by latency, and
+    // the extra resident warps of the smaller per-lane state outweigh the shorter scans of fewer, fatter lanes.
+    DDNERF_FAST(4, 1) DDNERF_FAST(4, 2) DDNERF_FAST(4, 4) DDNERF_FAST(8, 4) DDNERF_FAST(16, 4) DDNERF_FAST(32, 4) DDNERF_FAST(32, 8)
 #undef DDNERF_FAST
     return false;
 }

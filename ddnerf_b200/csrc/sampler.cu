@@ -7,6 +7,7 @@
 // stages its ray's weights/bins in shared memory, builds the smoothed CDF with a warp scan and
 // binary-searches it per sample: O(S + n log S) work and bins+weights+u in, samples out of HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -27,51 +28,62 @@ __device__ __forceinline__ float linspace01(int idx, int steps, float step) {   
 // chunk edges take them from the previous chunk's last / the next chunk's first value.  All of a ray's
 // random numbers are requested before the first is used (K chunks, compile time), otherwise the kernel is
 // bound by one DRAM latency per chunk.
-template <int K>
+// R rays per warp: the only way to keep enough bytes in flight -- one ray's (S+1) * 4 bytes per warp leave the
+// memory system idle most of the time.
+template <int K, int R>
 __global__ void __launch_bounds__(256) first_cycle_kernel(const float* __restrict__ near, const float* __restrict__ far,
                                                            int64_t ray_stride, const float* __restrict__ t_rand,
                                                            float* __restrict__ out, int64_t N, int S, int lindisp) {
     const int lane = threadIdx.x & 31;
-    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ray >= N) return;
+    const int64_t ray0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (ray0 >= N) return;
     const int steps = S + 1;
-    const float* rr = t_rand ? t_rand + ray * steps : nullptr;
-    float rnd[K];
+    float rnd[R][K], nrv[R], frv[R];
 #pragma unroll
-    for (int c = 0; c < K; ++c) rnd[c] = (rr && c * 32 + lane <= S) ? __ldg(rr + c * 32 + lane) : 0.f;
-    const float nr = __ldg(near + ray * ray_stride), fr = __ldg(far + ray * ray_stride);
+    for (int r = 0; r < R; ++r) {
+        const int64_t ray = min(ray0 + r, N - 1);
+        const float* rr = t_rand ? t_rand + ray * steps : nullptr;
+#pragma unroll
+        for (int c = 0; c < K; ++c) rnd[r][c] = (rr && c * 32 + lane <= S) ? __ldg(rr + c * 32 + lane) : 0.f;
+        nrv[r] = __ldg(near + ray * ray_stride); frv[r] = __ldg(far + ray * ray_stride);
+    }
     const float step = 1.0f / (float)S;
-    const float inr = lindisp ? 1.0f / nr : 0.f, ifr = lindisp ? 1.0f / fr : 0.f;
-    auto tv = [&](int k) {
-        k = min(max(k, 0), S);
-        float s = linspace01(k, steps, step);
-        return lindisp ? 1.0f / (inr * (1.0f - s) + ifr * s) : nr * (1.0f - s) + fr * s;
-    };
-    float* orow = out + ray * steps;
-    float cur = tv(lane), prev_last = cur;              // prev_last: value at index (chunk start - 1)
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-        const int i = c * 32 + lane;
-        if (c * 32 > S) break;
-        const float nxt_chunk = tv(i + 32);             // next chunk's values (clamped index)
-        float lo_n = __shfl_up_sync(FULL, cur, 1);      // t[i-1]
-        float hi_n = __shfl_down_sync(FULL, cur, 1);    // t[i+1]
-        const float next_first = __shfl_sync(FULL, nxt_chunk, 0);
-        if (lane == 0) lo_n = prev_last;
-        if (lane == 31) hi_n = next_first;
-        prev_last = __shfl_sync(FULL, cur, 31);
-        if (i <= S) {
-            float t = cur;
-            if (rr) {                                   // samplers.py:52-60
-                float lower = i == 0 ? cur : 0.5f * (cur + lo_n);
-                float upper = i == S ? cur : 0.5f * (hi_n + cur);
-                t = lower + (upper - lower) * rnd[c];
-                if (i == 0) t = nr;
-                if (i == S) t = fr;
+    for (int r = 0; r < R; ++r) {
+        if (ray0 + r >= N) break;
+        const float nr = nrv[r], fr = frv[r];
+        const float inr = lindisp ? 1.0f / nr : 0.f, ifr = lindisp ? 1.0f / fr : 0.f;
+        auto tv = [&](int k) {
+            k = min(max(k, 0), S);
+            float s = linspace01(k, steps, step);
+            return lindisp ? 1.0f / (inr * (1.0f - s) + ifr * s) : nr * (1.0f - s) + fr * s;
+        };
+        float* orow = out + (ray0 + r) * steps;
+        float cur = tv(lane), prev_last = cur;          // prev_last: value at index (chunk start - 1)
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            const int i = c * 32 + lane;
+            if (c * 32 > S) break;
+            const float nxt_chunk = tv(i + 32);         // next chunk's values (clamped index)
+            float lo_n = __shfl_up_sync(FULL, cur, 1);  // t[i-1]
+            float hi_n = __shfl_down_sync(FULL, cur, 1);// t[i+1]
+            const float next_first = __shfl_sync(FULL, nxt_chunk, 0);
+            if (lane == 0) lo_n = prev_last;
+            if (lane == 31) hi_n = next_first;
+            prev_last = __shfl_sync(FULL, cur, 31);
+            if (i <= S) {
+                float t = cur;
+                if (t_rand) {                           // samplers.py:52-60
+                    float lower = i == 0 ? cur : 0.5f * (cur + lo_n);
+                    float upper = i == S ? cur : 0.5f * (hi_n + cur);
+                    t = lower + (upper - lower) * rnd[r][c];
+                    if (i == 0) t = nr;
+                    if (i == S) t = fr;
+                }
+                orow[i] = t;
             }
-            orow[i] = t;
+            cur = nxt_chunk;
         }
-        cur = nxt_chunk;
     }
 }
 
@@ -526,8 +538,9 @@ bool dispatch_fast(int S, int n, F&& f) {
         if (n <= 9 * G) { f(std::integral_constant<int, G>{}, std::integral_constant<int, C>{}, std::integral_constant<int, 9>{}); return true; } \
         return false;                                                                                                       \
     }
-    // eight cells per lane wherever S allows: short rays share a warp
-    DDNERF_FAST(4, 1) DDNERF_FAST(4, 2) DDNERF_FAST(4, 4) DDNERF_FAST(4, 8) DDNERF_FAST(8, 8) DDNERF_FAST(16, 8) DDNERF_FAST(32, 8)
+    // Four cells per lane: measured faster than eight (profiles/r01b_*): these kernels are bound by latency, and
+    // the extra resident warps of the smaller per-lane state outweigh the shorter scans of fewer, fatter lanes.
+    DDNERF_FAST(4, 1) DDNERF_FAST(4, 2) DDNERF_FAST(4, 4) DDNERF_FAST(8, 4) DDNERF_FAST(16, 4) DDNERF_FAST(32, 4) DDNERF_FAST(32, 8)
 #undef DDNERF_FAST
     return false;
 }
@@ -543,9 +556,9 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_first_cycle(const float* near, const 
     DDNERF_CHECK_ARG(S >= 1, "sample_first_cycle: S=%d < 1", S);
     if (N == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (S + 1 <= 32 * 2) first_cycle_kernel<2><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
-    else if (S + 1 <= 32 * 5) first_cycle_kernel<5><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
-    else if (S + 1 <= 32 * 9) first_cycle_kernel<9><<<ceil_div(N, 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    if (S + 1 <= 32 * 2) first_cycle_kernel<2, 8><<<ceil_div(N, 8 * 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    else if (S + 1 <= 32 * 5) first_cycle_kernel<5, 4><<<ceil_div(N, 8 * 4), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    else if (S + 1 <= 32 * 9) first_cycle_kernel<9, 2><<<ceil_div(N, 8 * 2), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
     else first_cycle_generic_kernel<<<ceil_div(N * (S + 1), 256), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
     DDNERF_LAUNCHED("sample_first_cycle", 1);
     return 0;

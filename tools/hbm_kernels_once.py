@@ -4,7 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ddnerf_oracle as orc
-from ddnerf_b200 import ops
+from ddnerf_b200 import mlp_tc, ops
 from ddnerf_b200.rays import synth_rays
 N, S = int(sys.argv[1]), int(sys.argv[2])
 dev = torch.device("cuda:0")
@@ -20,6 +20,8 @@ sig = torch.rand(N, S, device=dev, generator=g) * 0.5 + 1e-3
 lt = 0.5 * (1 + torch.erf((0 - mus) / sig / 2 ** 0.5))
 pin = 0.5 * (1 + torch.erf((1 - mus) / sig / 2 ** 0.5)) - lt
 for _ in range(3):
+    t0 = ops.sample_first_cycle(rays[:, 7:8], rays[:, 8:9], S, False, u)
+    mlp_tc.encode_img(rays, t0)
     rawg = raw.clone().requires_grad_(True)
     out = ops.composite(rawg, t0, rays[:, 3:6], noise, 1.0, None, False, True, False)
     w = out[3].detach()
