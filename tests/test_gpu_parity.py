@@ -114,6 +114,63 @@ def test_resampler_indices_match_oracle(ops):
         close(s, s_ref, 1e-5, 2e-5)
 
 
+def _resample_inputs(N, S, seed, peaked):
+    g = torch.Generator().manual_seed(seed)
+    bins = torch.sort(torch.rand(N, S + 1, generator=g) * 4 + 2, dim=-1)[0]
+    bins[:, 0], bins[:, -1] = 2.0, 6.0
+    w = torch.rand(N, S, generator=g) ** (6 if peaked else 1)
+    if S >= 6:
+        w[:, S // 3: S // 2] = 0.0                   # empty space
+    mus = torch.rand(N, S, generator=g)
+    sig = torch.rand(N, S, generator=g) * 0.5 + 1e-3
+    lt = orc.normal_cdf((0 - mus) / sig)
+    pin = orc.normal_cdf((1 - mus) / sig) - lt
+    return g, bins, w, mus, sig, lt, pin
+
+
+# every lane-group shape of the fast path (S <= 256: G x C = 4x1 .. 32x8, K = 5 / 9), ragged S and N, and the
+# generic kernels behind them (S = 300; n > 9 G)
+@pytest.mark.parametrize("S,n", [(2, 9), (3, 4), (7, 8), (16, 17), (31, 32), (33, 34), (64, 65), (100, 101), (128, 129),
+                                 (128, 40), (200, 201), (256, 257), (300, 301), (16, 200)])
+@pytest.mark.parametrize("det", [True, False])
+def test_resamplers_shapes_vs_oracle(ops, S, n, det):
+    N = 37
+    g, bins, w, mus, sig, lt, pin = _resample_inputs(N, S, 100 + S + n, peaked=(S % 2 == 0))
+    rand = None if det else torch.rand(N, n, generator=g)
+    for pad in (True, False):
+        s_ref, _ = orc.sample_pdf(bins, w, n, pad, rand)
+        close(ops.sample_pdf(cu(bins), cu(w), n, pad, cu(rand)), s_ref, 1e-5, 2e-5)
+        d_ref, _ = orc.sample_pdf_with_mu_sigma(bins, w, mus, sig, pin, lt, n, pad, 2.0, 6.0, rand)
+        d = ops.sample_pdf_mu_sigma(cu(bins), cu(w), cu(mus), cu(sig), cu(pin), cu(lt), n, pad, 2.0, 6.0, cu(rand))
+        assert (d[:, 1:] >= d[:, :-1]).all()
+        # erfinv near its singularities amplifies 1-ulp cdf differences (see test_resamplers_golden): all but a
+        # handful of samples within 3e-4, none off by more than 5e-2 (depths are in [2,6])
+        err = (d.cpu() - d_ref).abs()
+        assert (err > 3e-4 + 1e-4 * d_ref.abs()).float().mean().item() < 2e-3 and err.max().item() < 5e-2
+
+
+def test_dd_resampler_sorts_when_bins_leave_cfg_range(ops):
+    """samplers.py:210-213: endpoints pinned to cfg near/far, then sorted -- exercised with a cfg range INSIDE the bins."""
+    N, S, n = 19, 32, 33
+    g, bins, w, mus, sig, lt, pin = _resample_inputs(N, S, 5, peaked=False)
+    rand = torch.rand(N, n, generator=g)
+    d_ref, _ = orc.sample_pdf_with_mu_sigma(bins, w, mus, sig, pin, lt, n, True, 3.0, 5.0, rand)
+    d = ops.sample_pdf_mu_sigma(cu(bins), cu(w), cu(mus), cu(sig), cu(pin), cu(lt), n, True, 3.0, 5.0, cu(rand))
+    assert (d[:, 1:] >= d[:, :-1]).all()
+    close(d, d_ref, 1e-4, 3e-4)
+
+
+@pytest.mark.parametrize("S", [1, 5, 16, 32, 33, 100, 128, 129, 257, 300])
+def test_first_cycle_shapes_vs_oracle(ops, S):
+    N = 45
+    g = torch.Generator().manual_seed(S)
+    near, far = torch.rand(N, 1, generator=g) + 1.5, torch.rand(N, 1, generator=g) + 5.0
+    rnd = torch.rand(N, S + 1, generator=g)
+    for lind in (False, True):
+        close(ops.sample_first_cycle(cu(near), cu(far), S, lind, cu(rnd)), orc.sample_first_cycle(near, far, S, lind, rnd), 1e-6, 1e-6)
+        close(ops.sample_first_cycle(cu(near), cu(far), S, lind), orc.sample_first_cycle(near, far, S, lind), 1e-6, 1e-6)
+
+
 # ---------------------------------------------------------------------------------------------
 # K2 encoding
 # ---------------------------------------------------------------------------------------------
@@ -267,6 +324,51 @@ def test_dp_loss_golden(ops, shape, wname, cname):
         ref = ref if key == "g_w0" else ref[:, :-1]
         sc = ref.abs().amax(dim=1, keepdim=True).clamp(min=1e-7)
         assert ((got.cpu() - ref).abs() / sc).max().item() < tol, key
+
+
+@pytest.mark.parametrize("S0,S1", [(2, 2), (3, 5), (7, 9), (16, 16), (33, 31), (64, 64), (100, 90), (128, 128), (128, 300),
+                                   (200, 210), (256, 256), (300, 300)])
+@pytest.mark.parametrize("blender", [True, False])
+def test_dp_loss_shapes_vs_oracle(ops, S0, S1, blender):
+    """Every lane-group shape of the fast path, ragged sizes and the generic fallback, forward and backward."""
+    N = 41
+    g, t0, w0, mus, sig, lt, pin = _resample_inputs(N, S0, 7 + S0 + S1, peaked=False)
+    w0 = w0 + 0.05
+    # wide in-cell Gaussians: with sigma ~ 1e-3 the estimated mass of most fine cells is 0 or one ulp of the CDF,
+    # a rounding coin flip inside log() in the reference itself (see test_dp_loss_golden, 'peaked')
+    sig = sig + 0.15
+    lt = orc.normal_cdf((0 - mus) / sig)
+    pin = orc.normal_cdf((1 - mus) / sig) - lt
+    # fine edges stop short of `far`: at t1 == far the estimated CDF is 1 +- 1 ulp and dd_utils.py:66 blocks or passes
+    # its gradient by a rounding coin flip in the reference itself (test_dp_loss_golden documents that knife edge)
+    t1 = torch.sort(torch.rand(N, S1 + 1, generator=g) * 3.8 + 2, dim=-1)[0]
+    t1[:, 0] = 2.0
+    w1 = torch.rand(N, S1, generator=g) + 0.05
+    if blender:
+        w1[3] = 0.0                                   # a ray the blender row filter drops (dd_utils.py:16)
+        lt = lt.clone()                               # the reference forgets to filter left_tails (DESIGN.md 2):
+        lt[3:] = lt[3:].roll(-1, 0)                   # feed it the rows it would actually pair up
+    a = [x.clone().requires_grad_(True) for x in (w0, mus, sig)]
+    ref = orc.estimate_dp_loss(t1, t0, w1, a[0], a[1], a[2], lt, pin, blender)
+    ref.backward()
+    # the same restatement in double: the yardstick for how far fp32 arithmetic alone moves these gradients
+    d = [x.double().clone().requires_grad_(True) for x in (w0, mus, sig)]
+    orc.estimate_dp_loss(t1.double(), t0.double(), w1.double(), d[0], d[1], d[2], lt.double(), pin.double(), blender).backward()
+    if blender:
+        lt_ours = lt.clone(); lt_ours[3:] = lt[3:].roll(1, 0)
+    else:
+        lt_ours = lt
+    b = [cu(x).clone().requires_grad_(True) for x in (w0, mus, sig)]
+    loss = ops.dp_loss(cu(t1), cu(t0), cu(w1), b[0], b[1], b[2], cu(lt_ours), cu(pin), blender)
+    close(loss, ref, 3e-4, 1e-6)
+    loss.backward()
+    for got, want, exact, tol in zip(b, a, d, (3e-2, 3e-3, 3e-3)):
+        gr, gw, gd = got.grad.cpu(), want.grad, exact.grad.float()
+        sc = gd.abs().amax(dim=1, keepdim=True).clamp(min=1e-7)
+        ours, theirs = ((gr - gd).abs() / sc).max().item(), ((gw - gd).abs() / sc).max().item()
+        # as accurate as the reference's own fp32 evaluation (which loses up to a few percent of a row's scale at
+        # S0 >= 128), or within the per-kernel budget
+        assert ours < max(tol, 3.0 * theirs), (ours, theirs)
 
 
 # ---------------------------------------------------------------------------------------------
