@@ -24,6 +24,8 @@ SOURCES = {
     "composite.cu": [],
     "sampler.cu": ["-fmad=false"],
     "encode.cu": ["-fmad=false"],
+    "raygen.cu": ["-fmad=false"],
+    "frame.cu": ["-fmad=false"],
     "dploss.cu": ["-fmad=false"],
     "mlp_f32.cu": [],
     "mlp_tc.cu": [],

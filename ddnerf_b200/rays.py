@@ -7,8 +7,9 @@ the same distributions as its datasets:
 * ``ndc_mipnerf_rays``    -- data_utils/dataset_helpers.py:3-42
 * ``pose_spherical``      -- data_utils/load_blender.py:12-41
 
-This is NOT on the per-step hot path (it is row f1, "next", of SURVEY.md section 8f); it only
-feeds it.
+Row f1 ("next") of SURVEY.md section 8f: ``ray_bundle_cuda`` is the device kernel (csrc/raygen.cu) the
+render loop uses; the tensor-level functions below restate the same arithmetic on the CPU to synthesise
+benchmark / test rays and to check the kernel.
 """
 import math
 
@@ -35,7 +36,11 @@ def pose_spherical(theta_deg, phi_deg, radius):
 
 
 def get_ray_bundle(height, width, focal, c2w):
-    """nerf_helpers.py:67-125 -> origins [H,W,3], directions [H,W,3] (un-normalised), radii [H,W,1]."""
+    """nerf_helpers.py:67-125 -> origins [H,W,3], directions [H,W,3] (un-normalised), radii [H,W,1].
+    A pose that lives on a CUDA device gets its rays from the device kernel (``ray_bundle_cuda``); a CPU pose
+    is the host-side restatement used to synthesise dataset-shaped workloads."""
+    if isinstance(c2w, torch.Tensor) and c2w.is_cuda:
+        return ray_bundle_cuda(height, width, focal, c2w, c2w.device)
     eps = 1e-5
     jj, ii = torch.meshgrid(torch.arange(height, dtype=c2w.dtype), torch.arange(width, dtype=c2w.dtype),
                             indexing="ij")
@@ -65,7 +70,8 @@ def ndc_project(H, W, focal, near, rays_o, rays_d):
 
 
 def ndc_mipnerf_rays(H, W, focal, rays_o, rays_d, near=1):
-    """dataset_helpers.py:3-42: forward-facing NDC rays + radii from neighbouring origins."""
+    """dataset_helpers.py:3-42: forward-facing NDC rays + radii from neighbouring origins.  (Tensor-level
+    restatement; the fused device path is ``ray_bundle_cuda(..., ndc_near=near)``.)"""
     o, d = ndc_project(H, W, focal, near, rays_o, rays_d)
     dx = torch.sqrt(torch.sum((o[:-1] - o[1:]) ** 2, -1))
     dx = torch.cat([dx, dx[-2:-1]])
@@ -73,6 +79,31 @@ def ndc_mipnerf_rays(H, W, focal, rays_o, rays_d, near=1):
     dy = torch.cat([dy, dy[:, -2:-1]], 1)
     radii = (0.5 * (dx + dy)) * 2 / math.sqrt(12)
     return o, d, radii[..., None]
+
+
+def ray_bundle_cuda(height, width, focal, c2w, device="cuda", rows=None, ndc_near=None):
+    """get_ray_bundle (and, with ``ndc_near`` set, ndc_mipnerf_rays on top of it) as ONE kernel on the device:
+    the frame's rays from the 12 floats of its pose, no meshgrid and no host->device copy of the rays.
+    ``rows=(lo, hi)`` restricts the output to those pixel rows (frame split across ranks).  Returns
+    (origins [rows,W,3], directions [rows,W,3], radii [rows,W,1]) as CUDA tensors."""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("ddnerf_b200: ray_bundle_cuda needs a CUDA device (the path has no CPU fallback)")
+    lo, hi = (0, height) if rows is None else rows
+    pose = (ctypes.c_float * 12)(*[float(x) for x in torch.as_tensor(c2w).detach().cpu().reshape(-1)[:12]])
+    with torch.cuda.device(dev):
+        ro = torch.empty(hi - lo, width, 3, device=dev)
+        rd = torch.empty(hi - lo, width, 3, device=dev)
+        rad = torch.empty(hi - lo, width, 1, device=dev)
+        _lib.check(lib.ddnerf_ray_bundle(height, width, float(focal), pose, int(ndc_near is not None),
+                                         float(ndc_near or 0.0), lo, hi, ctypes.c_void_p(ro.data_ptr()),
+                                         ctypes.c_void_p(rd.data_ptr()), ctypes.c_void_p(rad.data_ptr()),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ray_bundle")
+    return ro, rd, rad
 
 
 # Workload presets: (H, W, focal, c2w, near, far, ndc) -- SURVEY.md section 8d

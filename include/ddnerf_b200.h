@@ -179,6 +179,31 @@ int ddnerf_composite_backward(const float* raw, int raw_stride, const float* t, 
                               const float* g_weights, const float* g_depth, const float* g_cdisp,
                               float* g_raw, float* g_mus, int64_t N, int S, void* stream);
 
+/* ---- f1: ray generation (general_utils/nerf_helpers.py:67-125 get_ray_bundle; with ndc != 0 followed by
+ * data_utils/dataset_helpers.py:3-42 ndc_mipnerf_rays(H, W, focal, ro, rd, near = ndc_near)) ------------- */
+/* c2w_host: HOST pointer to the first 12 floats of the row-major 4x4 camera-to-world matrix (read during the
+ * call).  Pixel rows [row_lo, row_hi) of the H x W frame are written: ray_origins / ray_directions
+ * [rows, W, 3], radii [rows, W, 1] (directions un-normalised, as the reference returns them). */
+int ddnerf_ray_bundle(int H, int W, double focal, const float* c2w_host, int ndc, float ndc_near,
+                      int row_lo, int row_hi, float* ray_origins, float* ray_directions, float* radii,
+                      void* stream);
+
+/* Same with the pose in DEVICE memory (12 floats), so that a captured CUDA graph can be replayed for a new pose. */
+int ddnerf_ray_bundle_dev(int H, int W, double focal, const float* c2w_dev, int ndc, float ndc_near,
+                          int row_lo, int row_hi, float* ray_origins, float* ray_directions, float* radii,
+                          void* stream);
+
+/* ---- f4: frame post-processing (validation_utils/visualization.py:11-27 cast_to_disparity_image /
+ * cast_to_image; render_video.py:96-101 video frame) ---------------------------------------------------- */
+/* minmax[0..1] <- min, max of disp[0..n) (NaNs skipped).  workspace: >= 16 bytes, zeroed ONCE by the caller; the
+ * call leaves it zeroed again.  With a frame split across ranks the caller reduces minmax (MIN, MAX) between the
+ * two calls. */
+int ddnerf_frame_minmax(const float* disp, int64_t n, void* workspace, float* minmax, void* stream);
+/* rgb [rows*W,3], disp [rows*W] -> any of: rgb8 [rows,W,3] = trunc(clamp(255 rgb, 0, 255)); disp8 [rows,W] =
+ * trunc(255 clamp((disp - min)/(max - min), 0, 1)); video_bgr [rows, 2W, 3] = [rgb8 | disp8 x3] in BGR order. */
+int ddnerf_frame_pack_u8(const float* rgb, const float* disp, const float* minmax, uint8_t* rgb8, uint8_t* disp8,
+                         uint8_t* video_bgr, int rows, int W, void* stream);
+
 /* ---- K5: depth-distribution loss (models/dd_utils.py:6-78) ------------------------------- */
 /* scratch: >= 4 + 2*N floats of caller-owned workspace: [0] = sum of the per-ray KL values, [1] = number of
  * rays kept by the blender row filter (dd_utils.py:12-28), [4 .. 4+N) per-ray KL, [4+N .. 4+2N) per-ray kept

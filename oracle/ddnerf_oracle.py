@@ -372,6 +372,31 @@ def estimate_dp_loss(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_i
 
 
 # --------------------------------------------------------------------------------------------
+# frame post-processing (row f4)
+# --------------------------------------------------------------------------------------------
+def cast_to_disparity_image(disp):
+    """validation_utils/visualization.py:11-17 -> uint8 [H,W]."""
+    img = (disp - disp.min()) / (disp.max() - disp.min())
+    img = img.clamp(0, 1) * 255
+    return img.detach().cpu().numpy().astype("uint8")
+
+
+def cast_to_image(rgb):
+    """validation_utils/visualization.py:20-27 -> uint8 [H,W,3]: ToPILImage on a float tensor is mul(255).byte().
+    The clamp states what the renderer's range (-0.001 .. 1.001, volume_rendering_utils.py:25-27) needs; the
+    reference leaves the two out-of-range ends to the float->uint8 cast."""
+    return rgb.detach().cpu().mul(255).clamp(0, 255).byte().numpy()
+
+
+def video_frame(rgb, disp8):
+    """render_video.py:96-101 -> uint8 [H, 2W, 3], BGR: the colour image next to the grey disparity image."""
+    import numpy as np
+    rgb8 = cast_to_image(rgb)
+    d3 = np.repeat(disp8[..., None], 3, axis=-1)
+    return np.concatenate([rgb8[..., ::-1], d3], axis=1)
+
+
+# --------------------------------------------------------------------------------------------
 # model orchestration (models.py:40-162, 207-322)
 # --------------------------------------------------------------------------------------------
 def pack_rays(ro, rd, rad, near, far):

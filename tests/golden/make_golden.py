@@ -263,6 +263,26 @@ def stage_dp_loss():
         save(f"dp_loss_{S0}_{S1}", **arrs)
 
 
+def stage_rays():
+    """f1: get_ray_bundle (nerf_helpers.py:67-125) and ndc_mipnerf_rays (dataset_helpers.py:3-42) of the reference on
+    small frames: a rotated + translated pinhole pose, and a forward-facing pose through the NDC projection (even
+    width, identity rotation -> an exactly-zero direction component, the epsilon branch of :114-115)."""
+    from data_utils.dataset_helpers import ndc_mipnerf_rays as ref_ndc
+    from ddnerf_b200.rays import pose_spherical
+    out = {}
+    H, W, focal = 13, 18, 21.37
+    pose = pose_spherical(37.0, -25.0, 3.3)
+    ro, rd, rad = ref_helpers.get_ray_bundle(H, W, focal, pose)
+    out.update(p_H=H, p_W=W, p_focal=focal, p_pose=pose, p_ro=ro.clone(), p_rd=rd, p_rad=rad)
+    H, W, focal = 14, 20, 17.5
+    pose = torch.eye(4)
+    pose[:3, 3] = torch.tensor([0.11, -0.07, 0.02])
+    ro, rd, _ = ref_helpers.get_ray_bundle(H, W, focal, pose)
+    o, d, r = ref_ndc(H, W, focal, ro.clone(), rd, near=1)
+    out.update(n_H=H, n_W=W, n_focal=focal, n_pose=pose, n_ro=o, n_rd=d, n_rad=r, n_rd_cam=rd)
+    save("ray_bundle", **{k: (torch.tensor(v) if not isinstance(v, torch.Tensor) else v) for k, v in out.items()})
+
+
 def subsample_grads(prefix, module):
     out = {}
     for k, p in module.named_parameters():
@@ -322,9 +342,13 @@ def end_to_end():
 
 
 if __name__ == "__main__":
+    if "--rays-only" in sys.argv:
+        stage_rays()
+        sys.exit(0)
     stage_samplers()
     stage_encoding()
     stage_mlp()
     stage_render()
     stage_dp_loss()
+    stage_rays()
     end_to_end()

@@ -181,3 +181,21 @@ def test_end_to_end(tag):
     if pf is not None:
         for k in ("mus", "sigmas", "smoothed_sigmas"):
             close(out[0][k], g[f"out0_{k}"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# f1: the host-side restatement of the ray set-up (ddnerf_b200/rays.py) against the reference's own output
+# ---------------------------------------------------------------------------------------------
+def test_ray_bundle_restatement_golden():
+    from ddnerf_b200 import rays as R
+    g = load_golden("ray_bundle")
+    H, W, focal = int(g["p_H"]), int(g["p_W"]), float(g["p_focal"])
+    ro, rd, rad = R.get_ray_bundle(H, W, focal, g["p_pose"])
+    for got, key in ((ro, "p_ro"), (rd, "p_rd"), (rad, "p_rad")):
+        torch.testing.assert_close(got, g[key], rtol=1e-6, atol=1e-7)
+    H, W, focal = int(g["n_H"]), int(g["n_W"]), float(g["n_focal"])
+    ro, rd, _ = R.get_ray_bundle(H, W, focal, g["n_pose"])
+    torch.testing.assert_close(rd, g["n_rd_cam"], rtol=1e-6, atol=1e-7)
+    o, d, r = R.ndc_mipnerf_rays(H, W, focal, ro, rd, near=1)
+    for got, key in ((o, "n_ro"), (d, "n_rd"), (r.squeeze(-1), "n_rad")):
+        torch.testing.assert_close(got, g[key].reshape(got.shape), rtol=2e-6, atol=1e-6)
