@@ -148,7 +148,7 @@ def run_reference(args, cfg, kind, desc):
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{n}-ray batch of the workload per step, fwd+bwd, torch CPU fp32 oracle"},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_render(args, dev, world, rank, dist):
@@ -243,7 +243,28 @@ def run_render(args, dev, world, rank, dist):
             "frames": frames, "chunk_rays": int(cfg.nerf.validation.chunksize)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to fd 1 at
+    communicator set-up whenever NCCL_DEBUG >= VERSION, from the environment or nccl.conf), so keep a private copy of
+    the real stdout for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -276,10 +297,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            # the NCCL version banner (NCCL_DEBUG=VERSION, from the environment or nccl.conf) goes to stdout;
-            # stdout carries exactly one JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     os.environ["DDNERF_MLP_MODE"] = args.mlp_mode
@@ -430,7 +447,7 @@ def main():
                                 "sample": f"{n_cpu}-ray batch of the workload, fwd+bwd, 1 warm-up + 2 timed steps, "
                                           "torch CPU fp32 oracle"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
