@@ -34,6 +34,8 @@ SIGNATURES = {
     "ddnerf_ray_bundle_dev": (c_i, [c_i, c_i, ctypes.c_double, c_p, c_i, c_f, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ddnerf_frame_minmax": (c_i, [c_p, c_l, c_p, c_p, c_p]),
     "ddnerf_frame_pack_u8": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "ddnerf_raystore_pack": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p]),
+    "ddnerf_raystore_gather": (c_i, [c_p, c_l, c_p, c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ddnerf_find_interval": (c_i, [c_p, c_p, c_p, c_l, c_i, c_i, c_p]),
     "ddnerf_encode": (c_i, [c_p, c_p, c_p, c_l, c_p, c_l, c_l, c_i, c_i, c_p]),
     "ddnerf_mlp_f32_workspace_bytes": (c_l, [c_l]),

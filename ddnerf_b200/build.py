@@ -26,6 +26,7 @@ SOURCES = {
     "encode.cu": ["-fmad=false"],
     "raygen.cu": ["-fmad=false"],
     "frame.cu": ["-fmad=false"],
+    "raystore.cu": [],
     "dploss.cu": ["-fmad=false"],
     "mlp_f32.cu": [],
     "mlp_tc.cu": [],

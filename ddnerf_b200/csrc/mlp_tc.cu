@@ -111,10 +111,7 @@ __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const f
         for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(x[i]), neg, 1);     // bit i = sign of x[i]
     }
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        const float a = RELU ? fmaxf(x[i], 0.f) : x[i], c = RELU ? fmaxf(x[i + 1], 0.f) : x[i + 1];
-        pk[i / 2] = tc::pack_bf16(a, c);
-    }
+    for (int i = 0; i < 32; i += 2) pk[i / 2] = RELU ? tc::pack_bf16_relu(x[i], x[i + 1]) : tc::pack_bf16(x[i], x[i + 1]);
     store_chunk32(act_u32, row, c0, pk);
     return ~neg;
 }
@@ -239,11 +236,20 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
 
 __device__ __forceinline__ float masked(float x, uint32_t m, int bit) { return ((m >> bit) & 1u) ? x : 0.f; }
 
+// dZ = dA * relu'(Z): convert first, then clear the masked bf16 halves.  Four mask bits become the sign bits of the
+// four bytes of one register by a multiply (bit k -> bit 8k+7: 0x10204080 = 2^7 + 2^14 + 2^21 + 2^28, no carries),
+// and PRMT's sign-replicate mode spreads each into a 16-bit lane mask: 9 instructions per 4 values instead of 12.
 __device__ __forceinline__ void bwd_chunk32(const uint32_t (&v)[32], uint32_t m, int c0, uint32_t act_u32, int row) {
     uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 32; i += 2)
-        pk[i / 2] = tc::pack_bf16(masked(__uint_as_float(v[i]), m, i), masked(__uint_as_float(v[i + 1]), m, i + 1));
+    for (int i = 0; i < 32; i += 4) {
+        const uint32_t r = ((m >> i) & 15u) * 0x10204080u;
+        uint32_t w01, w23;
+        asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(w01) : "r"(r));
+        asm("prmt.b32 %0, %1, %1, 0xbbaa;" : "=r"(w23) : "r"(r));
+        pk[i / 2] = tc::pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1])) & w01;
+        pk[i / 2 + 1] = tc::pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])) & w23;
+    }
     store_chunk32(act_u32, row, c0, pk);
 }
 

@@ -232,5 +232,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ReLU and the bf16 conversion in one instruction (cvt.rn.relu: negative results clamp to +0, NaN stays NaN);
+// max(x, 0) followed by round-to-nearest gives the same bits for every non-NaN input.
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 }  // namespace tc
 }  // namespace ddnerf

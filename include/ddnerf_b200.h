@@ -204,6 +204,16 @@ int ddnerf_frame_minmax(const float* disp, int64_t n, void* workspace, float* mi
 int ddnerf_frame_pack_u8(const float* rgb, const float* disp, const float* minmax, uint8_t* rgb8, uint8_t* disp8,
                          uint8_t* video_bgr, int rows, int W, void* stream);
 
+/* ---- f3: device-resident training ray store (data_utils/dataset.py:8-59 TrainDataset) ----------------- */
+/* rows [n,12] <- {origin 3, direction 3, radius 1, target rgb 3, 0, 0} per ray (48-byte rows, 16-byte aligned). */
+int ddnerf_raystore_pack(const float* ray_origins, const float* ray_directions, const float* radii,
+                         const float* target_rgb, int64_t n, float* rows, void* stream);
+/* Batch i takes row base + idx[i] (dataset.py:52-53: origins[idxs], directions[idxs], radii[idxs], target[idxs]).
+ * idx: int64 on the device.  An index outside [0, total_rows) sets *bad_index_flag (may be null) and reads row 0. */
+int ddnerf_raystore_gather(const float* rows, int64_t total_rows, const int64_t* idx, int64_t n, int64_t base,
+                           float* ray_origins, float* ray_directions, float* radii, float* target_rgb,
+                           int* bad_index_flag, void* stream);
+
 /* ---- K5: depth-distribution loss (models/dd_utils.py:6-78) ------------------------------- */
 /* scratch: >= 4 + 2*N floats of caller-owned workspace: [0] = sum of the per-ray KL values, [1] = number of
  * rays kept by the blender row filter (dd_utils.py:12-28), [4 .. 4+N) per-ray KL, [4+N .. 4+2N) per-ray kept

@@ -263,6 +263,57 @@ def test_frame_renderer_pose_to_u8(ops):
 
 
 # ---------------------------------------------------------------------------------------------
+# f3 device-resident training ray store
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ndc", [False, True])
+def test_ray_store_matches_train_dataset(ops, ndc):
+    """dataset.py:8-59: vstack of every image's rays + targets, batch = rows[idxs]."""
+    from ddnerf_b200 import rays as R
+    from ddnerf_b200.raystore import DeviceRayStore
+    g = torch.Generator().manual_seed(3)
+    n_img, H, W, focal = 3, 10, 14, 12.5
+    poses = []
+    for k in range(n_img):
+        p = torch.eye(4) if ndc else R.pose_spherical(20.0 * k, -15.0, 3.0)
+        p = p.clone()
+        p[:3, 3] += torch.tensor([0.05 * k + 0.01, 0.02, 0.03])
+        poses.append(p)
+    poses = torch.stack(poses)
+    images = torch.rand(n_img, H, W, 3, generator=g)
+    ref = [[], [], [], []]
+    for k in range(n_img):
+        ro, rd, rad = R.get_ray_bundle(H, W, focal, poses[k])
+        if ndc:
+            ro, rd, rad = R.ndc_mipnerf_rays(H, W, focal, ro, rd, 1)
+        for lst, t in zip(ref, (ro.reshape(-1, 3), rd.reshape(-1, 3), rad.reshape(-1, 1), images[k].reshape(-1, 3))):
+            lst.append(t)
+    ref = [torch.vstack(x) for x in ref]
+    store = DeviceRayStore(poses, images, focal, ndc_rays=ndc)
+    assert len(store) == n_img * H * W
+    idxs = torch.randint(0, len(store), (257,), generator=g)
+    idxs[0], idxs[1] = 0, len(store) - 1
+    out = store.get_training_rays_for_next_iter(257, DEV, idxs=idxs)
+    for got, want in zip(out, ref):
+        close(got, want[idxs], 2e-6, 1e-6)
+    assert torch.equal(out[3].cpu(), ref[3][idxs])                       # targets are copied, not recomputed
+    # device-side draws: right shapes, every row is a row of the store
+    ro, rd, rad, tgt = store.get_training_rays_for_next_iter(1000, DEV)
+    assert ro.shape == (1000, 3) and rad.shape == (1000, 1) and tgt.shape == (1000, 3)
+    full = store.get_training_rays_for_next_iter(len(store), DEV, idxs=torch.arange(len(store)))
+    for i in range(50):
+        assert ((full[1] == rd[i]).all(1) & (full[3] == tgt[i]).all(1) & (full[2] == rad[i]).all(1)).any()
+    assert store.check_indices()
+    store.get_training_rays_for_next_iter(2, DEV, idxs=torch.tensor([0, len(store)]))
+    assert not store.check_indices()                                     # out-of-range index is flagged, not read
+    # single-image mode: rows of ONE image
+    s1 = DeviceRayStore(poses, images, focal, ndc_rays=ndc, single_image_mode=True)
+    sub = torch.randint(0, H * W, (64,), generator=g)
+    out1 = s1.get_training_rays_for_next_iter(64, DEV, idxs=sub, img_idx=2)
+    close(out1[0], ref[0][2 * H * W + sub], 2e-6, 1e-6)
+    assert torch.equal(out1[3].cpu(), ref[3][2 * H * W + sub])
+
+
+# ---------------------------------------------------------------------------------------------
 # K2 encoding
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["blender", "ff", "360"])

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round evidence on ONE GPU: GPU test suite, the bench line, the ncu launch list of the bench command and
+# `ncu --set full` summaries of the MLP kernels.  .ncu-rep files stay in /tmp; summaries land in gpurun_out/<tag>_*.
+#   bash tools/evidence.sh <tag>
+TAG=${1:-rXX}
+mkdir -p gpurun_out /tmp/ncu_$TAG
+python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -1 gpurun_out/${TAG}_pytest_gpu.log
+python bench.py > gpurun_out/${TAG}_bench_bf16.json 2> gpurun_out/${TAG}_bench_bf16.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench_bf16.err
+# launch list of the same command (eager steps so that every kernel is a separate launch)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-graph --no-render --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
+python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.md
+# full captures of the MLP kernels (micro-benchmark, 4096 rays x 128 samples)
+cap() {  # name regex skip extra-args
+  ncu --set full --clock-control none --import-source on -k "regex:$2" -c 1 -s $3 -f -o /tmp/ncu_$TAG/$1 \
+      python tools/bench_mlp_tc.py --rays 4096 --samples 128 --iters 1 $4 > gpurun_out/${TAG}_ncu_$1.log 2>&1
+  python tools/ncu_summary.py /tmp/ncu_$TAG/$1.ncu-rep > gpurun_out/${TAG}_ncu_$1.md 2>> gpurun_out/${TAG}_ncu_$1.log && echo "$1 ok"
+}
+cap mlp_tc_fwd_nosave "mlp_tc_chain_kernel<0>" 3 ""
+cap mlp_tc_fwd "mlp_tc_chain_kernel<0>" 3 "--save"
+cap mlp_tc_dx "mlp_tc_chain_kernel<1>" 2 "--save"
+cap mlp_tc_dw "mlp_tc_dw_kernel" 2 "--save"
