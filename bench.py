@@ -457,10 +457,10 @@ def main():
     if breakdown:
         line["roofline"]["breakdown"] = breakdown
         # DRAM bytes per step of the three MLP kernels from the committed ncu --set full captures
-        # (profiles/r01_ncu_mlp_tc_*.md: read + write per launch at 524,288 rows), scaled by rows
-        per_row = (2.90e9 + 2.73e9 + 5.81e9) / 524288.0
+        # (profiles/r01b_ncu_mlp_tc_{fwd,dx,dw}.md: read + write per launch at 524,288 rows), scaled by rows
+        per_row = ((0.244e9 + 2.650e9) + (0.175e9 + 2.558e9) + (5.810e9 + 0.009e9)) / 524288.0
         line["roofline"]["traffic"] = per_row * rows_step if args.mlp_mode == "bf16" else None
-        line["roofline"]["traffic_note"] = "dram__bytes_read+write of fwd/dx/dw from profiles/r01_ncu_mlp_tc_*.md, per step"
+        line["roofline"]["traffic_note"] = "dram__bytes_read+write of fwd/dx/dw from profiles/r01b_ncu_mlp_tc_*.md, per step"
     if not args.no_render:
         line["render"] = run_render(args, dev, world, rank, dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

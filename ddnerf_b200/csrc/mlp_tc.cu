@@ -92,7 +92,7 @@ constexpr int kEpiThreads = 256;
 // four 16-byte chunks of the act buffer.  Returns the ReLU mask (bit i set: value i has its sign bit
 // clear, i.e. is positive -- or +0, where passing the gradient is immaterial), collected with one
 // funnel shift per value.
-template <bool RELU>
+template <bool RELU, bool MASK = true>
 __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const float* __restrict__ bias_s, int c0,
                                                 uint32_t act_u32, int row) {
     uint32_t pk[16];
@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const f
         x[i + 2] = __uint_as_float(v[i + 2]) + b.z;
         x[i + 3] = __uint_as_float(v[i + 3]) + b.w;
     }
-    if (RELU) {
+    if (RELU && MASK) {                     // inference (no mask buffer) skips the 32 funnel shifts
 #pragma unroll
         for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(x[i]), neg, 1);     // bit i = sign of x[i]
     }
@@ -156,7 +156,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                     uint32_t mk[4] = {0u, 0u, 0u, 0u};
                     uint32_t va[32], vb[32];
                     tc::tmem_ld32(tmem_row + cb, va);
-                    if (E.relu) {
+                    if (E.relu && g.mask) {
 #pragma unroll
                         for (int c = 0; c < 4; c += 2) {                   // TMEM loads one chunk ahead of the math
                             tc::tmem_ld_wait();
@@ -165,6 +165,16 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                             tc::tmem_ld_wait();
                             if ((c + 2) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
                             if ((c + 1) * 32 < nc) mk[c + 1] = epi_chunk32<true>(vb, bias_s, cb + (c + 1) * 32, act_u32, row);
+                        }
+                    } else if (E.relu) {                                   // inference: no ReLU masks to collect
+#pragma unroll
+                        for (int c = 0; c < 4; c += 2) {
+                            tc::tmem_ld_wait();
+                            if ((c + 1) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 1) * 32, vb);
+                            if (c * 32 < nc) epi_chunk32<true, false>(va, bias_s, cb + c * 32, act_u32, row);
+                            tc::tmem_ld_wait();
+                            if ((c + 2) * 32 < nc) tc::tmem_ld32(tmem_row + cb + (c + 2) * 32, va);
+                            if ((c + 1) * 32 < nc) epi_chunk32<true, false>(vb, bias_s, cb + (c + 1) * 32, act_u32, row);
                         }
                     } else {                                               // fc_feat: no activation, no mask
 #pragma unroll
