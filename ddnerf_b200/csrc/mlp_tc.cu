@@ -124,6 +124,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
     const int n_epis = P.n_epis;
     uint32_t acc_phase = 0;                  // bit T: parity of acc_full[T]
     int stores = 0;                          // bulk stores issued by thread 0
+    const uint64_t pol_stream = tc::l2_policy_evict_first();     // saved tiles are not re-read before they leave L2
     uint32_t k = 0;                          // running epilogue count: parity selects the bias buffer
     unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
@@ -227,8 +228,8 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                     if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     if (g.save && E.save_layer >= 0) {
                         const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
-                        tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
-                                     E.save_bytes);
+                        tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
+                                          E.save_bytes, pol_stream);
                         tc::bulk_commit();
                         ++stores;
                     }
@@ -271,6 +272,7 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
     const int n_epis = P.n_epis;
     uint32_t acc_phase = 0;
     int stores = 0;
+    const uint64_t pol_stream = tc::l2_policy_evict_first();
     unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -370,7 +372,8 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                     if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
                     if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
-                    tc::bulk_s2g(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes, E.save_bytes);
+                    tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes, E.save_bytes,
+                                      pol_stream);
                     tc::bulk_commit();
                     ++stores;
                 }
@@ -389,6 +392,8 @@ template <int PI>
 __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
     const Program& P = c_prog[PI];
     const int n_loads = P.n_loads;                         // multiple of kSlots
+    // every CTA re-reads the 2.4 MB of packed weights for each work item: keep them in L2 against the streaming saves
+    const uint64_t pol_w = tc::l2_policy_evict_last(), pol_in = tc::l2_policy_evict_first();
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const uint8_t* enc = g.enc + (size_t)item * kEncItemBytes;
@@ -398,7 +403,7 @@ __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
             tc::mbar_wait(&ctl->empty[slot], phase ^ 1);
             const uint8_t* src = (L.kind == LOAD_W ? g.wimg : enc) + L.off;
             tc::mbar_expect_tx(&ctl->full[slot], L.bytes);
-            tc::bulk_g2s(ring + slot * kSlotBytes, src, L.bytes, &ctl->full[slot]);
+            tc::bulk_g2s_hint(ring + slot * kSlotBytes, src, L.bytes, &ctl->full[slot], L.kind == LOAD_W ? pol_w : pol_in);
             if (++slot == kSlots) { slot = 0; phase ^= 1; }
         }
     }
@@ -428,35 +433,46 @@ struct Issuer {
     }
 };
 
-// One K = 256 layer part: for h in {0,1}: for tile in {0,1}: stages 4h..4h+3.  Tile 0 waits for the
-// stages, tile 1 releases them; every stage = two K = 16 MMAs.
+// One K = 256 layer part: for h in {0,1}: for tile in {0,1}: stages 4h..4h+3.  Tile 0 waits for each stage right
+// before the two K = 16 MMAs that read it (waiting for all four up front left the last stage of a layer only ~700
+// cycles between the release of its ring slot and its deadline -- less than one L2 bulk fetch: the issuer spent a
+// third of its time waiting on the ring); tile 1 finds them resident and releases them.
 __device__ __forceinline__ void issue_h_part(Issuer& S, uint32_t idesc, bool commit_acc) {
     uint32_t slot[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        // ---- tile 0: stage by stage ----
+        if (h == 0) S.wait_act(0);
 #pragma unroll
-        for (int T = 0; T < 2; ++T) {
-            if (h == 0) S.wait_act(T);
-            if (T == 0) {
-#pragma unroll
-                for (int c = 4 * h; c < 4 * h + 4; ++c) slot[c] = S.wait_stage();
-            }
+        for (int c = 4 * h; c < 4 * h + 4; ++c) {
+            slot[c] = S.wait_stage();
             tc::tc_fence_after_sync();
             if (tc::elect_one()) {
-                const uint32_t d = S.tmem + (uint32_t)T * 256u;
-#pragma unroll
-                for (int c = 4 * h; c < 4 * h + 4; ++c) {
-                    const uint64_t a = ((uint64_t)kHi128 << 32) |
-                                       (uint64_t)(S.base16 + (uint32_t)T * (kActBytes >> 4) + (uint32_t)(c / 2) * 1024u + (uint32_t)(c % 2) * 4u);
-                    const uint64_t b = ((uint64_t)kHi64 << 32) | (uint64_t)(S.base16 + (kRingOff >> 4) + slot[c] * (kSlotBytes >> 4));
-                    tc::mma_f16_ss(d, a, b, idesc, c == 0 ? 0u : 1u);
-                    tc::mma_f16_ss(d, a + 2, b + 2, idesc, 1u);
-                    if (T == 1) tc::mma_commit_u32(S.empty0 + slot[c] * 8u);
-                }
-                if (h == 1 && commit_acc) tc::mma_commit_u32(S.acc0 + (uint32_t)T * 8u);
+                const uint64_t a = ((uint64_t)kHi128 << 32) | (uint64_t)(S.base16 + (uint32_t)(c / 2) * 1024u + (uint32_t)(c % 2) * 4u);
+                const uint64_t b = ((uint64_t)kHi64 << 32) | (uint64_t)(S.base16 + (kRingOff >> 4) + slot[c] * (kSlotBytes >> 4));
+                tc::mma_f16_ss(S.tmem, a, b, idesc, c == 0 ? 0u : 1u);
+                tc::mma_f16_ss(S.tmem, a + 2, b + 2, idesc, 1u);
+                if (c == 7 && commit_acc) tc::mma_commit_u32(S.acc0);
             }
             __syncwarp();
         }
+        // ---- tile 1: the four stages are resident ----
+        if (h == 0) S.wait_act(1);
+        tc::tc_fence_after_sync();
+        if (tc::elect_one()) {
+            const uint32_t d = S.tmem + 256u;
+#pragma unroll
+            for (int c = 4 * h; c < 4 * h + 4; ++c) {
+                const uint64_t a = ((uint64_t)kHi128 << 32) |
+                                   (uint64_t)(S.base16 + (kActBytes >> 4) + (uint32_t)(c / 2) * 1024u + (uint32_t)(c % 2) * 4u);
+                const uint64_t b = ((uint64_t)kHi64 << 32) | (uint64_t)(S.base16 + (kRingOff >> 4) + slot[c] * (kSlotBytes >> 4));
+                tc::mma_f16_ss(d, a, b, idesc, c == 0 ? 0u : 1u);
+                tc::mma_f16_ss(d, a + 2, b + 2, idesc, 1u);
+                tc::mma_commit_u32(S.empty0 + slot[c] * 8u);
+            }
+            if (h == 1 && commit_acc) tc::mma_commit_u32(S.acc0 + 8u);
+        }
+        __syncwarp();
     }
 }
 
