@@ -27,7 +27,8 @@ using namespace tcmlp;
 constexpr int kDwStages = 3;
 constexpr int kDwStageBytes = 65536;           // [A half tile 32 KB | B half tile 32 KB]
 constexpr int kDwThreads = 192;                // warp 0 producer, 1 MMA issuer, 2..5 SIMT + flush
-constexpr int kMaxWork = 160;
+constexpr int kMaxWork = 480;                  // work items (a CTA takes up to three)
+constexpr int kMaxCtas = 160;
 
 enum : int8_t { B_ACT = 0, B_XYZ = 1, B_DIRX = 2 };
 enum : int8_t { FLUSH_STD = 0, FLUSH_DIR = 1, FLUSH_HEADS = 2 };
@@ -61,8 +62,12 @@ __constant__ DwOp c_ops[kNumOps] = {
     {9, 0, 2, 1, B_DIRX, -1, 0, 10, 0, FLUSH_STD, {0, 0}, 283, 256, 128, 27, 16384 + 4096},
     {9, 2, 1, 1, B_ACT, 9, 2, 11, 0, FLUSH_HEADS, {0, 0}, 128, 0, 6, 128, 8192 + 16384},
 };
-// relative cost of one tile of each op (KB moved) for the work split
-const uint32_t h_op_weight[kNumOps] = {88, 128, 128, 128, 128, 128, 88, 128, 128, 128, 112, 40, 48};
+// Cost model of the work split, measured on a B200 with the kernel's own per-item cycle counters
+// (ddnerf_mlp_tc_dw_set_profile_buffer; all 148 CTAs streaming, 4096 tiles): cycles per tile of each op -- the bytes moved
+// (88 / 128 / 112 / 40 / 48 KB) plus about 800 cycles per tile that do not scale with them -- and cycles of one flush
+// (fp32 atomics of the op's [M x N] accumulator; 18 tiles' worth for a 256 x 256 layer).
+const uint32_t h_op_weight[kNumOps] = {3520, 4185, 4185, 4185, 4185, 4185, 3300, 4185, 4185, 4185, 3970, 2120, 2390};
+const uint32_t h_op_flush[kNumOps] = {26000, 74000, 74000, 74000, 74000, 74000, 26000, 74000, 74000, 74000, 37000, 3400, 1100};
 
 struct WorkItem { uint32_t op, t0, t1; };
 
@@ -75,11 +80,12 @@ struct DwArgs {
     int64_t rows;
     int n_tiles, C;
     int n_work;
+    unsigned long long* prof;   // diagnostic: per work item {op, tiles, cycles to the last MMA, cycles of the flush}
 };
-struct DwWork { WorkItem w[kMaxWork]; };
+struct DwWork { WorkItem w[kMaxWork]; uint16_t first[kMaxCtas + 1]; };   // CTA i: items first[i] .. first[i+1]-1
 
 struct __align__(16) DwCtl {
-    uint64_t full[kDwStages], empty[kDwStages], acc_done;
+    uint64_t full[kDwStages], empty[kDwStages], acc_done, acc_free;
     uint32_t tmem_base, pad;
 };
 constexpr int kDwSmemBytes = kDwStages * kDwStageBytes + (int)sizeof(DwCtl);
@@ -98,8 +104,7 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-__device__ void dw_producer(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCtl* ctl, uint8_t* ring) {
-    uint32_t s = 0, phase = 0;
+__device__ void dw_producer(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCtl* ctl, uint8_t* ring, uint32_t& s, uint32_t& phase) {
     const size_t layer_pitch = (size_t)g.n_tiles * kActBytes;
     for (uint32_t t = wk.t0; t < wk.t1; ++t) {
         const uint8_t* a_src = op.a_layer >= 0 ? g.dz + op.a_layer * layer_pitch + (size_t)t * kActBytes : nullptr;
@@ -126,15 +131,18 @@ __device__ void dw_producer(const DwArgs& g, const DwOp& op, const WorkItem wk, 
     }
 }
 
-__device__ void dw_mma(const DwOp& op, const WorkItem wk, DwCtl* ctl, uint32_t ring_u32) {
+__device__ void dw_mma(const DwOp& op, const WorkItem wk, DwCtl* ctl, uint32_t ring_u32, uint32_t& s, uint32_t& phase, int item) {
     const uint32_t tmem = ctl->tmem_base;
+    if (item > 0) {                         // the previous item's accumulator has been read out of TMEM
+        tc::mbar_wait(&ctl->acc_free, (uint32_t)(item - 1) & 1u);
+        tc::tc_fence_after_sync();
+    }
     // MN-major operand descriptors (tile image rows = K): SW128 blocks [rows x 64 features], LBO = block
     // pitch, SBO = 8 rows; SW64 blocks [rows x 32 features]
     constexpr uint64_t kD128 = tc::smem_desc(0, 8192, 1024, tc::LAYOUT_SW128);
     constexpr uint64_t kD64 = tc::smem_desc(0, 4096, 512, tc::LAYOUT_SW64);
     const uint32_t id_main = tc::idesc_bf16(128, op.b_blocks > 0 ? op.b_blocks * 64 : 256, 1, 1);
     const uint32_t id64 = tc::idesc_bf16(128, 64, 1, 1), id32 = tc::idesc_bf16(128, 32, 1, 1);
-    uint32_t s = 0, phase = 0;
     const uint32_t n_stages = (wk.t1 - wk.t0) * 2;
     for (uint32_t it = 0; it < n_stages; ++it) {
         tc::mbar_wait(&ctl->full[s], phase);
@@ -171,14 +179,15 @@ __device__ __forceinline__ uint32_t sw128_pair(uint32_t r, uint32_t c) {
     return r * 128u + ((((c >> 3) ^ r) & 7u) << 4) + ((c & 7u) << 1);
 }
 
-__device__ void dw_simt(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCtl* ctl, uint32_t ring_u32, int tid) {
+__device__ void dw_simt(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCtl* ctl, uint32_t ring_u32, int tid, uint32_t& s,
+                        uint32_t& phase, int item, int witem) {
     // bias gradients: thread tid sums columns 2 tid, 2 tid + 1 of the dZ half tiles
     float cs0 = 0.f, cs1 = 0.f;
     const uint32_t c2 = 2u * (uint32_t)tid;
     const uint32_t blk2 = (c2 >> 6) * 8192u, cc2 = c2 & 63u;
     const bool cs_on = op.colsum && (int)c2 < op.a_blocks * 64;
-    uint32_t s = 0, phase = 0;
     const uint32_t n_stages = (wk.t1 - wk.t0) * 2;
+    const long long t_start = g.prof ? clock64() : 0;
     for (uint32_t it = 0; it < n_stages; ++it) {
         tc::mbar_wait(&ctl->full[s], phase);
         if (cs_on) {
@@ -213,8 +222,9 @@ __device__ void dw_simt(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCt
             atomicAdd(db + c2 + 1, cs1);
         }
     }
-    tc::mbar_wait(&ctl->acc_done, 0);
+    tc::mbar_wait(&ctl->acc_done, (uint32_t)item & 1u);
     tc::tc_fence_after_sync();
+    const long long t_acc = g.prof ? clock64() : 0;
     // a warp may read the TMEM lane quarter (CTA warp index % 4): warps 2..5 -> quarters 2,3,0,1
     const int quarter = ((tid >> 5) + 2) & 3;
     const int lane = tid & 31;
@@ -244,6 +254,11 @@ __device__ void dw_simt(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCt
         }
     }
     tc::tc_fence_before_sync();
+    tc::mbar_arrive(&ctl->acc_free);         // TMEM may be overwritten by the CTA's next work item
+    if (g.prof && tid == 0) {
+        unsigned long long* o = g.prof + (size_t)witem * 4;
+        o[0] = wk.op; o[1] = wk.t1 - wk.t0; o[2] = (unsigned long long)(t_acc - t_start); o[3] = (unsigned long long)(clock64() - t_acc);
+    }
 }
 
 __global__ void __launch_bounds__(kDwThreads, 1) mlp_tc_dw_kernel(const DwArgs g, const DwWork work) {
@@ -251,12 +266,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) mlp_tc_dw_kernel(const DwArgs g
     uint8_t* ring = smem;
     DwCtl* ctl = reinterpret_cast<DwCtl*>(smem + kDwStages * kDwStageBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const WorkItem wk = work.w[blockIdx.x];
-    const DwOp op = c_ops[wk.op];
+    const int w0 = work.first[blockIdx.x], w1 = work.first[blockIdx.x + 1];
     if (threadIdx.x == 0) {
         if ((tc::smem_u32(smem) & 1023u) != 0) { printf("ddnerf mlp_tc_dw: shared memory is not 1024-byte aligned\n"); __trap(); }
         for (int s = 0; s < kDwStages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1 + 128); }
         tc::mbar_init(&ctl->acc_done, 1);
+        tc::mbar_init(&ctl->acc_free, 128);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, 512);
@@ -264,47 +279,71 @@ __global__ void __launch_bounds__(kDwThreads, 1) mlp_tc_dw_kernel(const DwArgs g
     __syncthreads();
     tc::tc_fence_after_sync();
 
-    if (warp == 0) { if (lane == 0) dw_producer(g, op, wk, ctl, ring); }
-    else if (warp == 1) dw_mma(op, wk, ctl, tc::smem_u32(ring));
-    else dw_simt(g, op, wk, ctl, tc::smem_u32(ring), threadIdx.x - 64);
+    // every role walks the CTA's work items in the same order; the ring position carries over from item to item
+    uint32_t s = 0, phase = 0;
+    for (int w = w0; w < w1; ++w) {
+        const WorkItem wk = work.w[w];
+        const DwOp op = c_ops[wk.op];
+        if (warp == 0) { if (lane == 0) dw_producer(g, op, wk, ctl, ring, s, phase); }
+        else if (warp == 1) dw_mma(op, wk, ctl, tc::smem_u32(ring), s, phase, w - w0);
+        else dw_simt(g, op, wk, ctl, tc::smem_u32(ring), threadIdx.x - 64, s, phase, w - w0, w);
+    }
 
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(ctl->tmem_base, 512);
 }
 
-// Split the SMs over the layer-ops in proportion to their bytes per tile; each CTA then takes a
-// contiguous tile range of its op.  Every (op, tile) pair is covered exactly once.
-int plan_work(uint32_t n_tiles, int sms, DwWork& work) {
-    sms = std::max(kNumOps, std::min(sms, kMaxWork));
-    uint32_t wsum = 0;
-    for (int o = 0; o < kNumOps; ++o) wsum += h_op_weight[o];
-    int cnt[kNumOps], total = 0;
-    for (int o = 0; o < kNumOps; ++o) {
-        cnt[o] = std::max(1, (int)((uint64_t)sms * h_op_weight[o] / wsum));
-        cnt[o] = (int)std::min<uint32_t>((uint32_t)cnt[o], n_tiles);
-        total += cnt[o];
-    }
-    while (total != sms) {                  // give to the most loaded / take from the least loaded op
-        int best = -1;
-        for (int o = 0; o < kNumOps; ++o) {
-            if (total < sms ? (uint32_t)cnt[o] >= n_tiles : cnt[o] <= 1) continue;
-            if (best < 0) { best = o; continue; }
-            const uint64_t lo = (uint64_t)h_op_weight[o] * cnt[best], lb = (uint64_t)h_op_weight[best] * cnt[o];
-            if (total < sms ? lo > lb : lo < lb) best = o;
+// Work split.  The (op, tile) pairs are laid on one line, op after op, and cut into at most `sms` pieces of equal
+// COST: a piece pays every tile's cycles plus one flush per op it touches, so a piece that crosses an op boundary (two
+// work items, run back to back by one CTA) gets fewer tiles.  The common piece cost is found by bisection.  (Round 1a
+// gave every op a whole number of CTAs: with 13 ops on 148 SMs the rounding alone left a 13:12 imbalance, and ncu
+// showed the SMs active for 71 % of the kernel's duration.)  Every (op, tile) pair is covered exactly once.
+// Returns the number of CTAs.
+int assign_pieces(uint32_t n_tiles, int sms, uint64_t budget, DwWork* work) {
+    int n_items = 0, n_ctas = 0, op = 0;
+    uint32_t tile = 0;
+    if (work) work->first[0] = 0;
+    while (op < kNumOps) {
+        if (n_ctas >= sms && !work) return sms + 1;                 // does not fit
+        uint64_t left = budget;
+        bool opened = false;
+        while (op < kNumOps) {
+            const uint64_t w = h_op_weight[op], f = h_op_flush[op];
+            // open an item of this op only if a few tiles fit behind its flush (or the piece is still empty)
+            if (opened && left < f + 4 * w) break;
+            const uint64_t room = left > f ? (left - f) / w : 0;
+            const uint32_t take = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(room, 1), n_tiles - tile);
+            if (work && n_items < kMaxWork) work->w[n_items] = WorkItem{(uint32_t)op, tile, tile + take};
+            ++n_items;
+            opened = true;
+            const uint64_t cost = f + w * take;
+            left = left > cost ? left - cost : 0;
+            tile += take;
+            if (tile == n_tiles) { ++op; tile = 0; } else break;    // the piece ends inside this op
+            if (left == 0) break;
         }
-        if (best < 0) break;
-        if (total < sms) { ++cnt[best]; ++total; } else { --cnt[best]; --total; }
-    }
-    int n_work = 0;
-    for (int o = 0; o < kNumOps; ++o)
-        for (int j = 0; j < cnt[o]; ++j) {
-            const uint32_t t0 = (uint32_t)((uint64_t)n_tiles * j / cnt[o]), t1 = (uint32_t)((uint64_t)n_tiles * (j + 1) / cnt[o]);
-            if (t1 > t0 && n_work < kMaxWork) work.w[n_work++] = WorkItem{(uint32_t)o, t0, t1};
+        ++n_ctas;
+        if (work) {
+            if (n_ctas > kMaxCtas) return -1;
+            work->first[n_ctas] = (uint16_t)std::min(n_items, kMaxWork);
         }
-    return n_work;
+    }
+    return n_ctas;
 }
 
+int plan_work(uint32_t n_tiles, int sms, DwWork& work) {
+    sms = std::max(1, std::min(sms, kMaxCtas));
+    uint64_t lo = 1, hi = 0;
+    for (int o = 0; o < kNumOps; ++o) hi += (uint64_t)h_op_weight[o] * n_tiles + h_op_flush[o];
+    while (lo < hi) {                                                  // smallest piece cost that needs <= sms pieces
+        const uint64_t mid = (lo + hi) / 2;
+        if (assign_pieces(n_tiles, sms, mid, nullptr) <= sms) hi = mid; else lo = mid + 1;
+    }
+    return assign_pieces(n_tiles, sms, lo, &work);
+}
+
+unsigned long long* g_dw_prof = nullptr;
 std::once_flag g_dw_once;
 int g_dw_rc = 0;
 
@@ -335,7 +374,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
 
     if (max_ctas > 0) sms = std::min(sms, max_ctas);
     DwWork work{};
-    const int n_work = plan_work(n_tiles, sms, work);
+    const int n_work = plan_work(n_tiles, sms, work);        // number of CTAs
     DwArgs g{};
     g.act = static_cast<const uint8_t*>(act_save);
     g.dz = static_cast<const uint8_t*>(dz_save);
@@ -346,8 +385,16 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
     g.n_tiles = (int)n_tiles;
     g.C = out_channels;
     g.n_work = n_work;
+    g.prof = g_dw_prof;
     mlp_tc_dw_kernel<<<n_work, kDwThreads, kDwSmemBytes, static_cast<cudaStream_t>(stream)>>>(g, work);
     DDNERF_LAUNCHED("mlp_tc_backward_dw", 1);
+    return 0;
+}
+
+/* Diagnostic hook: a device buffer of >= 4 * 480 uint64 receives, per work item of the next dW launches,
+ * {layer-op, tiles, cycles until its last MMA completed, cycles of its flush}; NULL switches it off. */
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_dw_set_profile_buffer(void* dev_u64) {
+    g_dw_prof = static_cast<unsigned long long*>(dev_u64);
     return 0;
 }
 
@@ -356,7 +403,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_dw_plan(int64_t rows, int sms, uint32_t* triples, int max_items) {
     DDNERF_CHECK_ARG(triples && rows >= 0 && sms > 0, "mlp_tc_dw_plan: bad arguments");
     DwWork work{};
-    const int n = rows == 0 ? 0 : plan_work((uint32_t)(ddnerf_mlp_tc_items(rows) * 2), sms, work);
+    const int n_ctas = rows == 0 ? 0 : plan_work((uint32_t)(ddnerf_mlp_tc_items(rows) * 2), sms, work);
+    const int n = n_ctas == 0 ? 0 : work.first[n_ctas];
     for (int i = 0; i < n && i < max_items; ++i) {
         triples[3 * i] = work.w[i].op;
         triples[3 * i + 1] = work.w[i].t0;

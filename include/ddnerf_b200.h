@@ -139,6 +139,10 @@ int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const v
  * (0 = consistent) and the (layer-op, tile range) split of backward_dw over `sms` SMs, written as
  * (op, first tile, end tile) uint32 triples; returns the number of work items. */
 int ddnerf_mlp_tc_program_check(void);
+/* Diagnostic hook of the dW kernel: a device buffer of >= 4 * 480 uint64 receives, per work item of the next
+ * launches, {layer-op, tiles, cycles until its last MMA completed, cycles of its flush}; NULL switches it off. */
+int ddnerf_mlp_tc_dw_set_profile_buffer(void* dev_u64);
+
 /* Diagnostic hook: a device buffer of >= 8 * n_SMs uint64 into which the chain kernels write per-CTA cycle
  * counters (issuer total / waiting on epilogues / waiting on ring stages, epilogues waiting on MMAs / busy /
  * count); NULL (default) switches the instrumentation off. */

@@ -120,6 +120,23 @@ def main():
                   f"epilogue busy {e_busy / max(n, 1):.0f} cyc each (store drain + barrier {e_pre / max(n, 1):.0f}, accumulator -> act buffer "
                   f"{e_work / max(n, 1):.0f}), waiting on MMA {e_wait / max(n, 1):.0f} cyc each, n={n:.0f}")
         lib.ddnerf_mlp_tc_set_profile_buffer(None)
+        if args.save:
+            import collections
+            pb = torch.zeros(4 * 480, device="cuda", dtype=torch.int64)
+            lib.ddnerf_mlp_tc_dw_set_profile_buffer(_p(pb))
+            dw()
+            torch.cuda.synchronize()
+            lib.ddnerf_mlp_tc_dw_set_profile_buffer(None)
+            rowsp = pb.view(480, 4).cpu().tolist()
+            per = collections.defaultdict(list)
+            for op, tiles, cyc, fl in rowsp:
+                if tiles > 0:
+                    per[op].append((tiles, cyc, fl))
+            for op in sorted(per):
+                v = per[op]
+                big = [x for x in v if x[0] > 20]
+                cpt = sum(x[1] for x in big) / max(sum(x[0] for x in big), 1)
+                print(f"dw op {op:2d}: items {len(v):3d} tiles {sum(x[0] for x in v):6d} cycles/tile {cpt:8.0f} flush {sum(x[2] for x in v) / len(v):8.0f} cyc/item")
 
 
 if __name__ == "__main__":
