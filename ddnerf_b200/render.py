@@ -3,7 +3,8 @@
     camera pose -> rays (csrc/raygen.cu) -> model.run_iter(mode="validation") -> 8-bit images (csrc/frame.cu)
 
 Rows f1 and f4 of SURVEY.md section 8f around the per-ray path.  ``FrameRenderer`` owns the static buffers of one
-frame size and, with ``use_graph=True``, replays the whole frame as ONE CUDA graph: the only host->device traffic
+frame size and, with ``use_graph=True``, replays the whole frame as ONE CUDA graph (with several ranks: two graphs
+around the one eagerly launched NCCL all-reduce that makes the disparity range a whole-frame range): the only host->device traffic
 of a frame is its 48-byte pose, the only device->host traffic the 8-bit images (4 bytes per pixel, 6 with the
 side-by-side video frame) instead of 28 bytes of rays in and 16 bytes of float images out per pixel.
 """
@@ -73,12 +74,14 @@ class FrameRenderer:
         # the masked mus/sigmas diagnostics of models.py:292-300 have data-dependent shapes (a host sync per pass);
         # the render loop never reads them
         model.record_distributions = False
-        self.use_graph = bool(use_graph) and world == 1     # the disparity range of a split frame needs a collective
-        self._graph = None
+        self.use_graph = bool(use_graph)
+        self._graph = None           # one GPU: the whole frame; several ranks: the part before the collective
+        self._graph_tail = None      # several ranks: the part after it
         self._calls = 0
         self.float_out = None
 
-    def _body(self):
+    def _head(self):
+        """pose -> rays -> model -> rank-local disparity range."""
         lib = _lib.load()
         self.pose_dev.copy_(self.pose_host, non_blocking=True)
         _lib.check(lib.ddnerf_ray_bundle_dev(self.H, self.W, self.focal, _p(self.pose_dev), int(self.ndc_near is not None),
@@ -86,18 +89,31 @@ class FrameRenderer:
                                              _p(self.rays[1]), _p(self.rays[2]), _stream()), "ray_bundle_dev")
         with torch.no_grad():
             out = self.model.run_iter(*self.rays, mode="validation")
-        rgb, disp = out[1]["rgb"], out[1]["disp"]
+        rgb, disp = out[1]["rgb"], out[1]["disp"].contiguous()
         self.float_out = (rgb, disp)
-        disp = disp.contiguous()
         _lib.check(lib.ddnerf_frame_minmax(_p(disp), disp.numel(), _p(self.ws), _p(self.minmax), _stream()), "frame_minmax")
-        if self.world > 1:                                   # whole-frame disparity range: MIN / MAX over the ranks
-            import torch.distributed as dist
-            dist.all_reduce(self.minmax[0:1], op=dist.ReduceOp.MIN)
-            dist.all_reduce(self.minmax[1:2], op=dist.ReduceOp.MAX)
-        frame_to_u8(rgb, disp, minmax=self.minmax, out=self.out_dev)
+        if self.world > 1:
+            self.minmax[0:1].neg_()                          # one MAX all-reduce of (-min, max) serves both ends
+
+    def _collective(self):
+        """Whole-frame disparity range when ranks render row blocks (the only collective of the render loop)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.minmax, op=dist.ReduceOp.MAX)
+
+    def _tail(self):
+        """8-bit conversion and the copies to the pinned host images."""
+        if self.world > 1:
+            self.minmax[0:1].neg_()
+        frame_to_u8(self.float_out[0], self.float_out[1], minmax=self.minmax, out=self.out_dev)
         for dst, src in zip(self.out_host, self.out_dev):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
+
+    def _body(self):
+        self._head()
+        if self.world > 1:
+            self._collective()
+        self._tail()
 
     def render(self, pose):
         """pose: 4x4 (or 3x4) camera-to-world, any device.  Synchronises the stream before returning."""
@@ -108,9 +124,20 @@ class FrameRenderer:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._body()
+                    if self.world == 1:
+                        self._body()
+                    else:
+                        self._head()
                 self._graph = g
+                if self.world > 1:                           # the NCCL call stays eager, between two graphs
+                    t = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(t, pool=g.pool()):
+                        self._tail()
+                    self._graph_tail = t
             self._graph.replay()
+            if self._graph_tail is not None:
+                self._collective()
+                self._graph_tail.replay()
         else:
             self._body()
         self._calls += 1
