@@ -65,9 +65,10 @@ __constant__ DwOp c_ops[kNumOps] = {
 // Cost model of the work split, measured on a B200 with the kernel's own per-item cycle counters
 // (ddnerf_mlp_tc_dw_set_profile_buffer; all 148 CTAs streaming, 4096 tiles): cycles per tile of each op -- the bytes moved
 // (88 / 128 / 112 / 40 / 48 KB) plus about 800 cycles per tile that do not scale with them -- and cycles of one flush
-// (fp32 atomics of the op's [M x N] accumulator; 18 tiles' worth for a 256 x 256 layer).
-const uint32_t h_op_weight[kNumOps] = {3520, 4185, 4185, 4185, 4185, 4185, 3300, 4185, 4185, 4185, 3970, 2120, 2390};
-const uint32_t h_op_flush[kNumOps] = {26000, 74000, 74000, 74000, 74000, 74000, 26000, 74000, 74000, 74000, 37000, 3400, 1100};
+// (fp32 reductions of the op's [M x N] accumulator, four columns per instruction where the rows are 16-byte aligned:
+// 4 tiles' worth for a 256 x 256 layer; 18 with scalar atomics).
+const uint32_t h_op_weight[kNumOps] = {3600, 4120, 4120, 4120, 4120, 4120, 3320, 4120, 4120, 4120, 3930, 2370, 2630};
+const uint32_t h_op_flush[kNumOps] = {6700, 17500, 17500, 17500, 17500, 17500, 6700, 17500, 17500, 17500, 29000, 3400, 1100};
 
 struct WorkItem { uint32_t op, t0, t1; };
 
@@ -247,9 +248,19 @@ __device__ void dw_simt(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCt
             tc::tmem_ld32(taddr + c0, v);
             tc::tmem_ld_wait();
             if (dst) {
+                // four columns per reduction where the row is 16-byte aligned (every 256- and 352-wide weight); the
+                // flush of a 256 x 256 accumulator was 65,536 scalar atomics = 18 tiles' worth of streaming time
+                if (((reinterpret_cast<uintptr_t>(dst + c0) & 15u) == 0) && c0 + 32 <= n_cols) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < n_cols) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(__uint_as_float(v[i])),
+                                     "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i < n_cols) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+                }
             }
         }
     }
