@@ -454,6 +454,11 @@ def main():
                                          "dx": "mlp_tc_chain_kernel<1> (dX chain)", "dw": "mlp_tc_dw_kernel (dW, db)"}[tag],
                               "bound": bound, "launches_per_step": len(by_tag[tag]) // K_ev, "ms_per_step": ms_step,
                               "achieved": ach, "peak": peak_v, "unit": unit, "frac": ach / peak_v})
+            if bound == "hbm":
+                # the denominator is the measured COPY bandwidth (half reads, half writes); this kernel only reads, and a
+                # read-only stream runs faster than a copy (DRAM bus turnarounds), so the fraction can pass 1
+                breakdown[-1]["peak_kind"] = "measured copy bandwidth (MEASURED_PEAKS.json); the kernel is a read-only stream"
+                breakdown[-1]["frac_of_spec_8TBs"] = ach / 8000.0
     if breakdown:
         line["roofline"]["breakdown"] = breakdown
         # DRAM bytes per step of the three MLP kernels from the committed ncu --set full captures
