@@ -93,6 +93,7 @@ class _MlpTc(torch.autograd.Function):
                                                  _stream()), "mlp_tc_forward")
         ctx.st, ctx.img, ctx.act, ctx.mask = st, img, act, mask
         ctx.rows, ctx.C = rows, C
+        ctx.sink = getattr(module, "_grad_sink", None)
         ctx.shapes = [tuple(p.shape) for p in params]
         return out
 
@@ -103,13 +104,19 @@ class _MlpTc(torch.autograd.Function):
         grad_out = _req(grad_out, "grad_out")
         dev = grad_out.device
         nw = len(ctx.shapes) // 2
-        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        views, off = [], 0
-        for s, n in zip(ctx.shapes, sizes):
-            views.append(flat[off:off + n].view(s))
-            off += n
-        gws, gbs = views[:nw], views[nw:]
+        if ctx.sink is not None:
+            # the trainer's flat gradient bucket: the dW kernel accumulates straight into it (both passes of a shared
+            # network, every chunk), so autograd neither allocates, clones, adds nor concatenates parameter gradients
+            gws, gbs = ctx.sink
+            views = [None] * len(ctx.shapes)
+        else:
+            sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+            views, off = [], 0
+            for s, n in zip(ctx.shapes, sizes):
+                views.append(flat[off:off + n].view(s))
+                off += n
+            gws, gbs = views[:nw], views[nw:]
         dz = torch.empty(ctx.act.numel(), device=dev, dtype=torch.uint8)
         table = _ptr_table(gws, gbs)
         with _mlp_timer("dx"):

@@ -36,9 +36,41 @@ class FlatBucket:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step = 0
+        self.sink = False
+
+    def install_sink(self):
+        """bf16 mode: let the weight-gradient kernel accumulate directly into this bucket's flat gradient (views in the
+        (weights, biases) order of the kernel's parameter table).  Replaces, per step, ~26 gradient clones / adds, the
+        zero fills of the per-call gradient buffers and the concatenation of `gather_grads` by one memset."""
+        if getattr(self.module, "mlp_mode", None) != "bf16" or not hasattr(self.module, "_param_pairs"):
+            return False
+        off, where = 0, {}
+        for p in self.params:
+            where[id(p)] = (off, p.numel(), p.shape)
+            off += p.numel()
+        def view(p):
+            o, n, shp = where[id(p)]
+            return self.grad[o:o + n].view(shp)
+        pairs = self.module._param_pairs()
+        object.__setattr__(self.module, "_grad_sink", ([view(w) for w, _ in pairs], [view(b) for _, b in pairs]))
+        self.sink = True
+        return True
+
+    def remove_sink(self):
+        if self.sink:
+            object.__setattr__(self.module, "_grad_sink", None)
+            self.sink = False
+
+    def begin_step(self):
+        """Before the forward of a step: with the sink installed the gradient bucket is an accumulator."""
+        if self.sink:
+            self.grad.zero_()
 
     def gather_grads(self):
-        """Copy the per-parameter .grad tensors into the flat gradient bucket (one cat kernel)."""
+        """Copy the per-parameter .grad tensors into the flat gradient bucket (one cat kernel).  With the sink
+        installed the kernels have already written there."""
+        if self.sink:
+            return
         torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params],
                   out=self.grad)
         for p in self.params:
@@ -130,6 +162,10 @@ class Trainer:
         """One iteration on the current stream: run_iter, losses, backward, gradient all-reduce, Adam."""
         tp = self.cfg.train_params
         self.model.train()
+        for b in self.buckets:
+            if not b.sink:
+                b.install_sink()                                 # (no-op unless the network runs in bf16 mode)
+            b.begin_step()
         out = self.model.run_iter(ray_origins, ray_directions, ray_rad, mode="train", rgb_target=target)
         coef = tp.loss_coeficients
         mse, g0, g1 = ops.mse_loss_and_grad(out[0]["rgb"], out[1]["rgb"], target, coef[0], coef[1])
