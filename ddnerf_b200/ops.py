@@ -235,6 +235,9 @@ class _Composite(torch.autograd.Function):
                                                 _p(cdisp), _p(rgb), N, S, _stream()), "composite_forward")
         ctx.save_for_backward(raw, t_vals, rd, noise, mus_c)
         ctx.cfg = (raw_stride, float(noise_std), bool(white_background), bool(blender), N, S)
+        # outputs nobody differentiates (disp, acc, depth, ... in a training step) arrive as None in backward instead of
+        # freshly zero-filled tensors: no fill kernels, and the backward kernel skips their terms
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(*([rgb] if rgb is not None else []))
         return rgb_map, disp, acc, weights, depth, cdisp, rgb
 
@@ -244,6 +247,8 @@ class _Composite(torch.autograd.Function):
         raw, t_vals, rd, noise, mus = ctx.saved_tensors
         raw_stride, noise_std, white, blender, N, S = ctx.cfg
         gs = [None if g is None else g.contiguous().float() for g in (g_rgb_map, g_disp, g_acc, g_weights, g_depth, g_cdisp)]
+        if all(g is None for g in gs):
+            return (None,) * 9
         g_raw = torch.empty(N, S, 4, device=raw.device, dtype=torch.float32)
         want_mus = mus is not None and ctx.needs_input_grad[5]
         g_mus = torch.empty(N, S, device=raw.device, dtype=torch.float32) if want_mus else None
