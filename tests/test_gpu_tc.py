@@ -394,3 +394,57 @@ def test_trainer_cuda_graph_matches_eager(pname):
     # learning-rate step either way: compare against the step size (lr ~ 5e-6 at these iterations), not ulp
     assert (w0 - w1).abs().max().item() < 2e-4
     assert torch.nn.functional.cosine_similarity((w0 - w0.mean()).double(), (w1 - w1.mean()).double(), dim=0).item() > 0.999999
+
+
+@pytest.mark.parametrize("pname", ["config_blender_mipnerf", "config_360"])
+def test_gradient_sink_equals_autograd_gradients(pname):
+    """FlatBucket.install_sink(): the dW kernel accumulating straight into the trainer's flat gradient bucket gives the
+    gradients autograd would have left in p.grad (both passes of the shared mip-NeRF network, both DDNeRF networks)."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    from ddnerf_b200.trainer import FlatBucket
+    dev = torch.device("cuda:0")
+    N, s0, s1 = 384, 32, 32
+    ro, rd, rad, near, far = synth_rays("blender" if "blender" in pname else "360", N, seed=9)
+    g = torch.Generator().manual_seed(2)
+    target = torch.rand(N, 3, generator=g).to(dev)
+    rnd = dict(t_rand=torch.rand(N, s0 + 1, generator=g), noise0=torch.randn(N, s0, generator=g),
+               u_rand=torch.rand(N, s1 + 1, generator=g), noise1=torch.randn(N, s1, generator=g))
+    grads = []
+    for sink in (False, True):
+        cfg, _ = preset(pname, num_coarse=s0, num_fine=s1)
+        is_dd = cfg.nerf.type == "DDNerfModel"
+        model = getattr(M, cfg.nerf.type)(cfg)
+        model.coarse.load_state_dict(orc.init_mlp_params(is_dd, seed=21))
+        nets = [model.coarse]
+        if is_dd:
+            model.fine.load_state_dict(orc.init_mlp_params(False, seed=22))
+            nets.append(model.fine)
+        for net in nets:
+            net.mlp_mode = "bf16"
+        model.to(dev)
+        model.record_distributions = False
+        model.randoms = {k: v.to(dev) for k, v in rnd.items()}
+        buckets = [FlatBucket(net) for net in nets]
+        for b in buckets:
+            if sink:
+                assert b.install_sink()
+            b.begin_step()
+        model.train()
+        out = model.run_iter(ro.to(dev), rd.to(dev), rad.to(dev), mode="train", rgb_target=target)
+        loss = sum(torch.nn.functional.mse_loss(out[j]["rgb"], target) for j in range(2))
+        if is_dd:
+            loss = loss + 0.1 * out[1]["dp_loss"].mean()
+        loss.backward()
+        if sink:
+            assert all(p.grad is None for b in buckets for p in b.params)
+        for b in buckets:
+            b.gather_grads()
+        grads.append(torch.cat([b.grad.clone() for b in buckets]).cpu())
+    a, s = grads
+    assert torch.isfinite(s).all() and s.abs().max() > 0
+    # same kernels, same operands; only the order of the fp32 atomic accumulation differs
+    assert ((a - s).abs().max() / a.abs().max()).item() < 1e-4
+    assert torch.nn.functional.cosine_similarity(a.double(), s.double(), dim=0).item() > 0.9999999
