@@ -448,3 +448,50 @@ def test_gradient_sink_equals_autograd_gradients(pname):
     # same kernels, same operands; only the order of the fp32 atomic accumulation differs
     assert ((a - s).abs().max() / a.abs().max()).item() < 1e-4
     assert torch.nn.functional.cosine_similarity(a.double(), s.double(), dim=0).item() > 0.9999999
+
+
+def _decode_enc_image(img, rows):
+    """Rows of the chain kernels' encoded operand image back to [rows, 96] IPE and [rows, 32] direction features
+    (layout: DESIGN.md section 3 -- per 256-row item [T0 xyz0,xyz1 | T1 xyz0,xyz1 | T0 xyz2 | T1 xyz2 | T0 dir | T1 dir],
+    blocks of [128 rows x 32 bf16], K-major SWIZZLE_64B)."""
+    raw = img.cpu().numpy().view(np.uint16)
+    n_items = (rows + 255) // 256
+    ipe = np.zeros((n_items * 256, 96), dtype=np.uint16)
+    dirs = np.zeros((n_items * 256, 32), dtype=np.uint16)
+    r = np.arange(128)
+    for it in range(n_items):
+        base = it * 32768                                    # uint16 units (64 KB per item)
+        for T in range(2):
+            for b in range(4):
+                off = {0: T * 8192, 1: T * 8192 + 4096, 2: 16384 + T * 4096, 3: 24576 + T * 4096}[b]
+                for j in range(4):
+                    col = (j ^ ((r >> 1) & 3)) * 8
+                    src = base + off + r * 32
+                    vals = np.stack([raw[src + col + k] for k in range(8)], 1)        # [128, 8]
+                    dst_rows = it * 256 + T * 128 + r
+                    if b < 3:
+                        ipe[dst_rows, b * 32 + j * 8: b * 32 + j * 8 + 8] = vals
+                    else:
+                        dirs[dst_rows, j * 8: j * 8 + 8] = vals
+    to_f = lambda u: torch.from_numpy((u.astype(np.uint32) << 16).view(np.float32).copy())
+    return to_f(ipe)[:rows], to_f(dirs)[:rows]
+
+
+@pytest.mark.parametrize("kind,N,S", [("blender", 37, 16), ("ff", 64, 32), ("360", 9, 128)])
+def test_encode_img_vs_oracle(kind, N, S):
+    """K2 in bf16 mode: every feature of the operand image within one bf16 step of the oracle's fp32 encoding
+    (integrated positional encoding, math_utils.py:112-166, and the view-direction encoding, nerf_helpers.py:127-171)."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200 import mlp_tc
+    from ddnerf_b200.rays import synth_rays
+    ro, rd, rad, near, far = synth_rays(kind, N, seed=11)
+    rays = orc.pack_rays(ro, rd, rad, near, far)
+    g = torch.Generator().manual_seed(5)
+    t = orc.sample_first_cycle(torch.full((N, 1), near), torch.full((N, 1), far), S, False, torch.rand(N, S + 1, generator=g))
+    ref = orc.encode_rows(rays, t)                                       # [N*S, 123] fp32
+    img = mlp_tc.encode_img(rays.cuda(), t.cuda())
+    ipe, dirs = _decode_enc_image(img, N * S)
+    for got, want in ((ipe, ref[:, :96]), (dirs[:, :27], ref[:, 96:])):
+        err = (got - want).abs()
+        assert (err <= 2.0 ** -8 * want.abs() + 3e-5).all(), err.max().item()
+    assert (dirs[:, 27:] == 0).all()
