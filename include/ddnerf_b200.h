@@ -136,8 +136,9 @@ int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const v
                               int out_channels, int max_ctas, void* stream);
 
 /* Host-only consistency hooks (no device work): the static ring/op programs of the chain kernels
- * (0 = consistent) and the (layer-op, tile range) split of backward_dw over `sms` SMs, written as
- * (op, first tile, end tile) uint32 triples; returns the number of work items. */
+ * (0 = consistent) and the split of backward_dw over `sms` SMs: the (layer-op, tile) line cut into at most `sms`
+ * equal-cost pieces, a piece that crosses a layer-op boundary being two (rarely three) work items run back to back by
+ * one CTA; written as (op, first tile, end tile) uint32 triples; returns the number of work items (<= sms + 12). */
 int ddnerf_mlp_tc_program_check(void);
 /* Diagnostic hook of the dW kernel: a device buffer of >= 4 * 480 uint64 receives, per work item of the next
  * launches, {layer-op, tiles, cycles until its last MMA completed, cycles of its flush}; NULL switches it off. */
