@@ -67,6 +67,7 @@ SIGNATURES = {
     "ddnerf_mse_loss": (c_i, [c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_p]),
     "ddnerf_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_i, c_f, c_p]),
     "ddnerf_adam_step_dev": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p]),
+    "ddnerf_train_schedule": (c_i, [c_p, c_p, ctypes.POINTER(ctypes.c_double), c_p]),
 }
 
 _lib = None

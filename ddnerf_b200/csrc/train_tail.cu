@@ -68,10 +68,56 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
     }
 }
 
+// The per-iteration scalars of the driver loop (train_model.py:135-150: annealed gaussian_smooth_factor, learning_rate_decay)
+// and Adam's bias corrections, computed ON THE DEVICE from a device-resident iteration counter: a replayed CUDA graph of the
+// training step then reads nothing the host mutates between replays (a pinned host buffer rewritten in place races with the
+// copy node of an earlier, still queued replay).  One thread, double arithmetic (what the Python driver does), then the
+// counters advance.  state = {iteration i, Adam step count t}; hyper = {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t),
+// grad_scale, gaussian_smooth_factor}.
+struct SchedArgs {
+    double lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult;
+    double beta1, beta2, eps, grad_scale;
+    double smooth0, dsmooth, final_smooth, finnish_smooth;
+};
+
+__global__ void schedule_kernel(long long* __restrict__ state, float* __restrict__ hyper, const SchedArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long i = state[0], t = state[1] + 1;
+    double delay = 1.0;
+    if (a.lr_delay_steps > 0) {
+        const double x = fmin(fmax((double)i / a.lr_delay_steps, 0.0), 1.0);
+        delay = a.lr_delay_mult + (1.0 - a.lr_delay_mult) * sin(0.5 * 3.14159265358979323846 * x);
+    }
+    const double u = fmin(fmax((double)i / a.max_steps, 0.0), 1.0);
+    const double lr = delay * exp(log(a.lr_init) * (1.0 - u) + log(a.lr_final) * u);
+    hyper[0] = (float)lr;
+    hyper[1] = (float)a.beta1;
+    hyper[2] = (float)a.beta2;
+    hyper[3] = (float)a.eps;
+    hyper[4] = (float)(1.0 - pow(a.beta1, (double)t));
+    hyper[5] = (float)sqrt(1.0 - pow(a.beta2, (double)t));
+    hyper[6] = (float)a.grad_scale;
+    hyper[7] = (float)((double)i < a.finnish_smooth ? a.smooth0 - a.dsmooth * (double)i : a.final_smooth);
+    state[0] = i + 1;
+    state[1] = t;
+}
+
 }  // namespace
 }  // namespace ddnerf
 
 using namespace ddnerf;
+
+extern "C" DDNERF_EXPORT int ddnerf_train_schedule(int64_t* state, float* hyper, const double* sched, void* stream) {
+    DDNERF_CHECK_ARG(state && hyper && sched, "train_schedule: null pointer");
+    SchedArgs a;
+    a.lr_init = sched[0]; a.lr_final = sched[1]; a.max_steps = sched[2]; a.lr_delay_steps = sched[3]; a.lr_delay_mult = sched[4];
+    a.beta1 = sched[5]; a.beta2 = sched[6]; a.eps = sched[7]; a.grad_scale = sched[8];
+    a.smooth0 = sched[9]; a.dsmooth = sched[10]; a.final_smooth = sched[11]; a.finnish_smooth = sched[12];
+    DDNERF_CHECK_ARG(a.lr_init > 0 && a.lr_final > 0 && a.max_steps > 0, "train_schedule: lr_init, lr_final and max_steps must be positive");
+    schedule_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(state), hyper, a);
+    DDNERF_LAUNCHED("train_schedule", 1);
+    return 0;
+}
 
 extern "C" DDNERF_EXPORT int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, float coef0, float coef1,
                                float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N, void* stream) {
@@ -91,8 +137,8 @@ extern "C" DDNERF_EXPORT int ddnerf_adam_step(float* param, const float* grad, f
     DDNERF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     DDNERF_CHECK_ARG(step >= 1, "adam_step: step=%d must be >= 1", step);
     if (n == 0) return 0;
-    float bc1 = 1.0f - powf(beta1, (float)step);
-    float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                         eps, bc1, bc2_sqrt, grad_scale);

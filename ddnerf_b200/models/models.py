@@ -101,7 +101,16 @@ class GeneralMipNerfModel(torch.nn.Module):
                 radiance_field, t_vals, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
                 white_background=mcfg.white_background, cfg=self.cfg, noise=self._rnd(f"noise{i}"), want_rgb=False)
             ret[i] = {"rgb": rgb, "disp": disp, "acc": acc, "weights": weights, "depth": depth}
+            self._record_t(i, t_vals)
         return ret
+
+    def _record_t(self, i, t_vals):
+        """Debug hook of the parity tests: with ``self.keep_t_vals = True`` the fence-posts of both passes of every chunk
+        are kept in ``self.last_t_vals[pass]`` (list over chunks); off by default."""
+        if getattr(self, "keep_t_vals", False):
+            if i == 0 and getattr(self, "_chunk_rows", (0, 0))[0] == 0:
+                self.last_t_vals = {0: [], 1: []}
+            self.last_t_vals[i].append(t_vals.detach())
 
     def run_network(self, ray_batch, t_vals, network, mode):
         """models.py:117-142: [N,12] rays + [N,S+1] fence-posts -> [N,S,C] raw radiance field."""
@@ -194,6 +203,8 @@ class DDNerfModel(GeneralMipNerfModel):
         t1 = sample_pdf_with_mu_sigma(t0, w0, mus, smoothed_sigmas, smoothed_part_inside, smoothed_left_tail,
                                       mcfg.num_fine + 1, self.cfg, det=(mcfg.perturb == 0.0),
                                       rand=self._rnd("u_rand")).detach()
+        self._record_t(0, t0)
+        self._record_t(1, t1)
         rf1 = self.run_network(ray_batch, t1, self.fine, mode)
         rgb1, disp1, acc1, w1, depth1, _, _ = volume_render_radiance_field(
             rf1, t1, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,

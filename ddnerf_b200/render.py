@@ -79,11 +79,15 @@ class FrameRenderer:
         self._graph_tail = None      # several ranks: the part after it
         self._calls = 0
         self.float_out = None
+        self.empty = self.hi <= self.lo      # more ranks than pixel rows: this rank only takes part in the collective
 
     def _head(self):
         """pose -> rays -> model -> rank-local disparity range."""
         lib = _lib.load()
         self.pose_dev.copy_(self.pose_host, non_blocking=True)
+        if self.empty:
+            self.minmax.fill_(float("-inf"))                 # neutral element of the MAX all-reduce of (-min, max)
+            return
         _lib.check(lib.ddnerf_ray_bundle_dev(self.H, self.W, self.focal, _p(self.pose_dev), int(self.ndc_near is not None),
                                              float(self.ndc_near or 0.0), self.lo, self.hi, _p(self.rays[0]),
                                              _p(self.rays[1]), _p(self.rays[2]), _stream()), "ray_bundle_dev")
@@ -102,6 +106,8 @@ class FrameRenderer:
 
     def _tail(self):
         """8-bit conversion and the copies to the pinned host images."""
+        if self.empty:
+            return
         if self.world > 1:
             self.minmax[0:1].neg_()
         frame_to_u8(self.float_out[0], self.float_out[1], minmax=self.minmax, out=self.out_dev)
@@ -121,6 +127,13 @@ class FrameRenderer:
         self.model.eval()
         if self.use_graph and self._calls >= 2:
             if self._graph is None:
+                # the packed bf16 weight images are refreshed by a host-side decision (TcState.refresh): capture with the
+                # state dirty so the pack kernels are nodes of the graph and every replay renders the CURRENT weights
+                # (a Trainer step or load_state_dict between frames would otherwise leave the graph on stale images)
+                for net in {id(self.model.coarse): self.model.coarse, id(self.model.fine): self.model.fine}.values():
+                    st = getattr(net, "_tc_state", None)
+                    if st is not None:
+                        st.dirty = True
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):

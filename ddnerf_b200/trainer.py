@@ -8,8 +8,6 @@ all-reduce (rays shard across ranks, weights are replicated) and applied by one 
 The per-parameter ``nn.Parameter`` objects (names, shapes, ``state_dict``) stay what the
 reference's checkpoints expect.
 """
-import math
-
 import torch
 import torch.distributed as dist
 
@@ -83,7 +81,53 @@ class FlatBucket:
         if st is not None:
             st.dirty = True
 
+    def check_alias(self):
+        """`module.to()` / `.float()` after construction re-allocates the parameters; Adam would then update only the
+        flat buffer and the model would silently stop learning."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        for p in self.params:
+            if not (lo <= p.data_ptr() < hi):
+                raise RuntimeError("ddnerf_b200: a parameter no longer aliases the trainer's flat bucket (module.to() / "
+                                   "load of a different device after Trainer construction?); build the Trainer last")
+
+    # ---- torch.optim.Adam interchange (train_model.py:110-118, 249-258) ---------------------------------
+    def state_dict(self, lr=0.0005):
+        """This bucket's optimizer state in the layout of ``torch.optim.Adam.state_dict()`` over
+        ``module.parameters()``: what the reference stores as ``optimizer_{1,2}_state_dict``."""
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            if self.step > 0:
+                state[i] = {"step": torch.tensor(float(self.step)),
+                            "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+            off += n
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Inverse of ``state_dict``; accepts what ``torch.optim.Adam.state_dict()`` wrote for the same module."""
+        state, off, steps = sd["state"], 0, set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            st = state.get(i, state.get(str(i)))
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            off += n
+        if len(steps) > 1:
+            raise RuntimeError(f"ddnerf_b200: per-parameter Adam step counts differ ({sorted(steps)}); one flat bucket "
+                               "steps all parameters together")
+        self.step = steps.pop() if steps else 0
+
     def adam(self, lr, grad_scale=1.0):
+        self.check_alias()
         self.step += 1
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step, grad_scale=grad_scale)
         self.mark_dirty()
@@ -115,19 +159,26 @@ class Trainer:
     ``use_graph=True`` captures the whole iteration (about 160 kernel launches and as many host-side
     dispatches) into ONE CUDA graph after two eager iterations and replays it from then on; the values that
     change every iteration -- learning rate, Adam bias corrections, the annealed ``gaussian_smooth_factor`` --
-    live in device memory and are refreshed by copy nodes inside the graph.  The graph is re-captured when
-    ``pdf_padding`` flips (train_model.py:140-142) or the batch shape changes.  The results are those of the
-    eager path: the same kernels in the same order."""
+    are computed ON THE DEVICE by the graph's first node from a device-resident iteration counter
+    (``ddnerf_train_schedule``), so a replay reads nothing the host mutates and any number of replays may be
+    queued without a host sync.  With several ranks the NCCL all-reduce is captured into the same graph.  The
+    graph is re-captured when ``pdf_padding`` flips (train_model.py:140-142) or the batch shape changes.  The
+    results are those of the eager path: the same kernels in the same order."""
 
     GRAPH_WARMUP = 2
 
-    def __init__(self, model, train_iters=200001, distributed=None, use_graph=False):
+    def __init__(self, model, train_iters=None, distributed=None, use_graph=False):
         self.model = model
         self.cfg = model.cfg
         self.is_dd = self.cfg.nerf.type == "DDNerfModel"
         self.buckets = [FlatBucket(model.coarse)]
         if self.is_dd:                                          # train_model.py:93-98 second optimizer
             self.buckets.append(FlatBucket(model.fine))
+        if train_iters is None:
+            try:
+                train_iters = int(self.cfg.experiment.train_iters)
+            except Exception:
+                train_iters = 200001
         self.train_iters = train_iters
         self.iter = 0
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
@@ -137,6 +188,11 @@ class Trainer:
         self._dsmooth = (tp.gaussian_smooth_factor - tp.final_smooth) / tp.finnish_smooth
         model.record_distributions = False
         self.use_graph = bool(use_graph)
+        # several ranks: capture the NCCL all-reduce into the step graph (one graph per step); False = two graphs around
+        # an eagerly launched all-reduce (round-1 behaviour)
+        self.capture_collective = True
+        self._counter_iter = -1
+        self._eager_calls = 0
         self._graph = None
         self._graph_tail = None
         self._graph_key = None
@@ -144,8 +200,33 @@ class Trainer:
         dev = self.buckets[0].flat.device
         if self.use_graph:
             # [lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, gaussian_smooth_factor]
-            self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
             self._hyper_dev = torch.zeros(8, device=dev, dtype=torch.float32)
+            self._sched_state = torch.zeros(2, device=dev, dtype=torch.int64)      # {iteration, Adam steps taken}
+
+    # ---- checkpoints in the reference's format (train_model.py:248-263 save, :77-81,110-118 resume) ---------------
+    def state_dict(self, loss=None, psnr=None):
+        """The dict ``train_model.py`` saves every ``save_every`` iterations (after iteration ``self.iter - 1``)."""
+        ck = {"iter": self.iter - 1, "model_1_state_dict": self.model.coarse.state_dict(),
+              "optimizer_1_state_dict": self.buckets[0].state_dict(self.lr(max(self.iter - 1, 0))), "loss": loss, "psnr": psnr}
+        if self.is_dd:
+            ck["model_2_state_dict"] = self.model.fine.state_dict()
+            ck["optimizer_2_state_dict"] = self.buckets[1].state_dict(self.lr(max(self.iter - 1, 0)))
+        return ck
+
+    def resume(self, checkpoint):
+        """Continue from a checkpoint written by the reference's driver or by ``state_dict``: weights, Adam moments and
+        step counts, ``start_iter = iter + 1`` and the ``pdf_padding`` fix-up of train_model.py:116-118."""
+        self.model.load_weights_from_checkpoint(checkpoint)
+        for k, b in enumerate(self.buckets):
+            sd = checkpoint.get(f"optimizer_{k + 1}_state_dict")
+            if sd is not None:
+                b.load_state_dict(sd)
+            b.mark_dirty()
+        self.iter = int(checkpoint["iter"]) + 1
+        if self.iter > self.cfg.train_params.max_pdf_pad_iters:
+            self.cfg.train_params.pdf_padding = False
+        self._graph = None                                     # re-capture: the device counters restart from here
+        return self.iter
 
     def lr(self, i):
         return learning_rate_decay(i, 0.0005, 5e-6, self.train_iters, lr_delay_steps=2500, lr_delay_mult=0.01)
@@ -158,7 +239,7 @@ class Trainer:
             tp.pdf_padding = False
         return smooth, self.lr(i)
 
-    def _body(self, ray_origins, ray_directions, ray_rad, target, lr, hyper=None):
+    def _body(self, ray_origins, ray_directions, ray_rad, target, lr, hyper=None, collective_inside=True):
         """One iteration on the current stream: run_iter, losses, backward, gradient all-reduce, Adam."""
         tp = self.cfg.train_params
         self.model.train()
@@ -179,8 +260,8 @@ class Trainer:
         torch.autograd.backward(tensors, grads)
         for b in self.buckets:
             b.gather_grads()
-        if hyper is not None and self.distributed and self.world > 1:
-            return loss, mse                                     # graph mode: the collective and Adam follow outside
+        if hyper is not None and self.distributed and self.world > 1 and not collective_inside:
+            return loss, mse                                     # two-graph mode: the collective and Adam follow outside
         allreduce_gradients(self.buckets, self.world if self.distributed else 1)
         self._optimize(lr, hyper)
         return loss, mse
@@ -197,33 +278,44 @@ class Trainer:
         host sync)."""
         i, tp = self.iter, self.cfg.train_params
         smooth, lr = self._schedule(i)
-        if not self.use_graph or i < self.GRAPH_WARMUP:
+        if not self.use_graph or self._eager_calls < self.GRAPH_WARMUP:
             tp.gaussian_smooth_factor = smooth
             loss, mse = self._body(ray_origins, ray_directions, ray_rad, target, lr)
             self.iter += 1
+            self._eager_calls += 1
             return loss, mse
 
         # ---- graphed iteration ------------------------------------------------------------------
-        t = i + 1                                              # Adam step count of this iteration (all buckets in lock step)
-        h = self._hyper_host
-        h[0], h[1], h[2], h[3] = lr, 0.9, 0.999, 1e-8
-        h[4], h[5] = 1.0 - 0.9 ** t, math.sqrt(1.0 - 0.999 ** t)
-        h[6], h[7] = 1.0 / self.world, smooth
         key = (bool(tp.pdf_padding), tuple(ray_origins.shape), tuple(target.shape), ray_origins.device)
-        if self._graph is None or key != self._graph_key:
+        if self._graph is None or key != self._graph_key or self._counter_iter != i:
             self._capture(key, ray_origins, ray_directions, ray_rad, target, lr)
         for dst, src in zip(self._static["in"], (ray_origins, ray_directions, ray_rad, target)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
-        if self._graph_tail is not None:                       # data parallel: NCCL all-reduce between two graphs
+        if self._graph_tail is not None:                       # data parallel without graph-captured NCCL: eager all-reduce
             allreduce_gradients(self.buckets, self.world)
             self._graph_tail.replay()
         for b in self.buckets:
             b.step += 1
             b.mark_dirty()
         self.iter += 1
+        self._counter_iter = self.iter                         # the device counter advanced inside the graph
+        tp.gaussian_smooth_factor = smooth                     # host copy for validation renders between iterations
         return self._static["loss"], self._static["mse"]
+
+    def _schedule_dev(self):
+        """Graph node: {lr, Adam bias corrections, grad_scale, smooth} of the device-side iteration counter."""
+        import ctypes
+        from . import _lib
+        tp = self.cfg.train_params
+        f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))      # the eager kernels take these as fp32 arguments
+        sched = (ctypes.c_double * 13)(0.0005, 5e-6, float(self.train_iters), 2500.0, 0.01, f32(0.9), f32(0.999), f32(1e-8),
+                                       f32(1.0 / self.world), float(self._smooth0), float(self._dsmooth),
+                                       float(tp.final_smooth), float(tp.finnish_smooth))
+        _lib.check(_lib.load().ddnerf_train_schedule(ctypes.c_void_p(self._sched_state.data_ptr()),
+                                                     ctypes.c_void_p(self._hyper_dev.data_ptr()), sched, ops._stream()),
+                   "train_schedule")
 
     def _capture(self, key, ray_origins, ray_directions, ray_rad, target, lr):
         tp = self.cfg.train_params
@@ -234,22 +326,35 @@ class Trainer:
             for p in b.params:
                 p.grad = None
             b.mark_dirty()                                     # the graph re-packs the bf16 weight images every replay
+            b.check_alias()
+        steps = {b.step for b in self.buckets}
+        if len(steps) != 1:
+            raise RuntimeError(f"ddnerf_b200: the buckets' Adam step counts differ ({sorted(steps)})")
+        # the device-side counters start where the host stands (first capture, re-capture, resume)
+        self._sched_state.copy_(torch.tensor([self.iter, steps.pop()], dtype=torch.int64))
+        self._counter_iter = self.iter
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         smooth_dev = self._hyper_dev[7]                        # 0-dim view: `sigmas * gaussian_smooth_factor` reads device memory
         saved = tp.gaussian_smooth_factor
-        with torch.cuda.graph(graph):
-            self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
-            tp.gaussian_smooth_factor = smooth_dev if self.is_dd else saved
-            loss, mse = self._body(*self._static["in"], lr, hyper=self._hyper_dev)
-        tp.gaussian_smooth_factor = float(saved) if not isinstance(saved, torch.Tensor) else float(self._hyper_host[7])
+        if isinstance(saved, torch.Tensor):
+            saved = float(saved)
+        nccl_in_graph = self.distributed and self.world > 1 and self.capture_collective
+        try:
+            with torch.cuda.graph(graph):
+                self._schedule_dev()
+                tp.gaussian_smooth_factor = smooth_dev if self.is_dd else saved
+                loss, mse = self._body(*self._static["in"], lr, hyper=self._hyper_dev, collective_inside=nccl_in_graph)
+        finally:
+            tp.gaussian_smooth_factor = saved
         self._static["loss"], self._static["mse"] = loss, mse
         self._graph_tail = None
-        if self.distributed and self.world > 1:                # the collective is launched eagerly between two graphs
+        if self.distributed and self.world > 1 and not nccl_in_graph:   # the collective launched eagerly between two graphs
             allreduce_gradients(self.buckets, self.world)
             torch.cuda.synchronize()
             tail = torch.cuda.CUDAGraph()
             with torch.cuda.graph(tail, pool=graph.pool()):
                 self._optimize(lr, hyper=self._hyper_dev)
             self._graph_tail = tail
+        # capture ran no kernels: the counters still hold this iteration
         self._graph, self._graph_key = graph, key

@@ -254,6 +254,15 @@ int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp
 int ddnerf_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                          int64_t n, const float* hyper, void* stream);
 
+/* The per-iteration host scalars of the driver loop, train_model.py:135-150 (annealed gaussian_smooth_factor,
+ * learning_rate_decay of general_utils/nerf_helpers.py:211-245) and Adam's bias corrections, computed on the device
+ * from a device-resident counter so that a replayed CUDA graph of the step reads nothing the host mutates.
+ * state[2] (int64, device) = {iteration i, Adam steps taken}: read, then both advanced by one.
+ * hyper[8] (device) receives {lr(i), beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, smooth(i)}, t = steps + 1.
+ * sched[13] (HOST doubles, read at call time) = {lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult, beta1,
+ * beta2, eps, grad_scale, smooth0, dsmooth, final_smooth, finnish_smooth}. */
+int ddnerf_train_schedule(int64_t* state, float* hyper, const double* sched, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,36 @@ def stage_rays():
     save("ray_bundle", **{k: (torch.tensor(v) if not isinstance(v, torch.Tensor) else v) for k, v in out.items()})
 
 
+def stage_frame():
+    """f4: cast_to_image / cast_to_disparity_image of the reference (validation_utils/visualization.py:11-27) and the video
+    frame assembly of its render loop (render_video.py:96-101, executed from the reference's own source text) on a small
+    synthetic frame whose colours cover the renderer's full range [-0.001, 1.001] (volume_rendering_utils.py:25-27).
+    ``matplotlib`` and ``imageio`` are not installed here; the module only uses them for plots / file output, so empty
+    stand-ins are registered before the import."""
+    import textwrap
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "imageio"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from validation_utils import visualization as ref_vis
+    import cv2
+    g = torch.Generator().manual_seed(11)
+    H, W = 23, 37
+    rgb = torch.rand(H, W, 3, generator=g) * 1.002 - 0.001
+    rgb[0, 0] = torch.tensor([-0.001, 1.001, 0.5])
+    rgb[0, 1] = torch.tensor([1.0, 0.0, 254.5 / 255.0])
+    rgb[0, 2] = torch.tensor([1.0 / 255.0, 2.0 / 255.0 - 1e-7, 0.99999])
+    disp = 1.0 / (torch.rand(H, W, generator=g) * 4.0 + 0.2)
+    img = ref_vis.cast_to_image(rgb[..., :3])                       # [3,H,W] uint8
+    d8 = ref_vis.cast_to_disparity_image(disp)                       # [1,H,W] uint8
+    # render_video.py:78-101: the frame written to the video (disp = cast_to_disparity_image(disp).squeeze())
+    lines = open("/root/reference/render_video.py").read().splitlines()[97:103]
+    assert lines[0].strip().startswith("rgb = 255*rgb") and lines[-1].strip().startswith("frame = cv2.cvtColor"), lines
+    scope = {"rgb": rgb.clone(), "disp": d8.squeeze(), "torch": torch, "np": np, "cv2": cv2}
+    exec(textwrap.dedent("\n".join(lines)), scope)
+    save("frame_post", rgb=rgb, disp=disp, rgb8_chw=img, disp8=d8, video_bgr=scope["frame"])
+
+
 def subsample_grads(prefix, module):
     out = {}
     for k, p in module.named_parameters():
@@ -345,10 +375,14 @@ if __name__ == "__main__":
     if "--rays-only" in sys.argv:
         stage_rays()
         sys.exit(0)
+    if "--frame-only" in sys.argv:
+        stage_frame()
+        sys.exit(0)
     stage_samplers()
     stage_encoding()
     stage_mlp()
     stage_render()
     stage_dp_loss()
     stage_rays()
+    stage_frame()
     end_to_end()

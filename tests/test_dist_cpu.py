@@ -106,3 +106,43 @@ def test_render_row_sharding(H, world):
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
         assert a1 == b0 and a0 <= a1
     assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_flat_bucket_state_dict_has_torch_adam_layout():
+    """FlatBucket.state_dict() is what torch.optim.Adam.state_dict() holds for the same parameters (the reference's
+    optimizer_{1,2}_state_dict, train_model.py:110-118,249-258): it loads into a real Adam, and a real Adam's state loads back."""
+    params = orc.init_mlp_params(False, seed=2)
+    net = _Net(params)
+    b = FlatBucket(net)
+    g = torch.Generator().manual_seed(0)
+    b.exp_avg.copy_(torch.randn(b.flat.shape, generator=g))
+    b.exp_avg_sq.copy_(torch.rand(b.flat.shape, generator=g))
+    b.step = 7
+    sd = b.state_dict(lr=1e-4)
+    ref = _Net(params)
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-4)
+    opt.load_state_dict(sd)
+    assert opt.param_groups[0]["lr"] == 1e-4 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    off = 0
+    for p in ref.parameters():
+        st = opt.state[p]
+        assert float(st["step"]) == 7.0
+        assert torch.equal(st["exp_avg"].reshape(-1), b.exp_avg[off:off + p.numel()])
+        assert torch.equal(st["exp_avg_sq"].reshape(-1), b.exp_avg_sq[off:off + p.numel()])
+        off += p.numel()
+    b2 = FlatBucket(_Net(params))
+    b2.load_state_dict(opt.state_dict())
+    assert b2.step == 7 and torch.equal(b2.exp_avg, b.exp_avg) and torch.equal(b2.exp_avg_sq, b.exp_avg_sq)
+    # a fresh optimizer (no steps yet) round-trips to zero moments
+    b3 = FlatBucket(_Net(params))
+    b3.load_state_dict(torch.optim.Adam(_Net(params).parameters()).state_dict())
+    assert b3.step == 0 and not b3.exp_avg.any()
+
+
+def test_flat_bucket_detects_re_allocated_parameters():
+    net = _Net(orc.init_mlp_params(False, seed=2))
+    b = FlatBucket(net)
+    b.check_alias()
+    net.double()                                         # re-allocates every parameter (what module.to(other device) does)
+    with pytest.raises(RuntimeError, match="no longer aliases"):
+        b.check_alias()

@@ -149,6 +149,64 @@ def test_resamplers_shapes_vs_oracle(ops, S, n, det):
         assert (err > 3e-4 + 1e-4 * d_ref.abs()).float().mean().item() < 2e-3 and err.max().item() < 5e-2
 
 
+def _error_distributions(got, ref32, exact):
+    """Sorted |error| of the CUDA result and of the reference's own fp32 evaluation, both against exact (fp64) arithmetic
+    on the same fp32 inputs."""
+    e_got = np.sort((got.double() - exact).abs().flatten().numpy())
+    e_ref = np.sort((ref32.double() - exact).abs().flatten().numpy())
+    return e_got, e_ref
+
+
+@pytest.mark.parametrize("S,n", [(16, 17), (32, 33), (64, 65), (128, 129)])
+@pytest.mark.parametrize("det", [True, False])
+def test_dd_resampler_error_vs_fp64_yardstick(ops, S, n, det):
+    """sample_pdf_with_mu_sigma (samplers.py:124-215) puts Phi^-1 behind a CDF interpolation: near z -> 0 / 0.999 and where
+    (c1 - c0) is tiny, one ulp of the CDF moves a sample by far more than one ulp, in the reference's own fp32 evaluation
+    as much as in the kernel.  Yardstick: the same formulas in float64 on the same fp32 inputs.  The kernel's error
+    DISTRIBUTION (every quantile, up to the maximum) must be no worse than 3x the distribution of the reference's fp32
+    errors, with a floor of three ulps of the depth range; 4096 rays per case (both smoothing branches, flat and peaked
+    weights with empty space, sigmas down to 1e-3)."""
+    N = 4096
+    worst = 0.0
+    for peaked in (False, True):
+        g, bins, w, mus, sig, lt, pin = _resample_inputs(N, S, 900 + S + int(peaked), peaked=peaked)
+        rand = None if det else torch.rand(N, n, generator=g)
+        for pad in (True, False):
+            args32 = (bins, w, mus, sig, pin, lt)
+            ref32, _ = orc.sample_pdf_with_mu_sigma(*args32, n, pad, 2.0, 6.0, rand)
+            exact, _ = orc.sample_pdf_with_mu_sigma(*[a.double() for a in args32], n, pad, 2.0, 6.0,
+                                                    None if rand is None else rand.double())
+            got = ops.sample_pdf_mu_sigma(*[cu(a) for a in args32], n, pad, 2.0, 6.0, cu(rand)).cpu()
+            assert (got[:, 1:] >= got[:, :-1]).all()
+            e_got, e_ref = _error_distributions(got, ref32, exact)
+            floor = 3 * 4.8e-7                                        # 3 ulp at depth 6
+            ratio = float(np.max(e_got / (3.0 * e_ref + floor)))
+            worst = max(worst, ratio)
+            q = [0.5, 0.99, 0.999, 1.0]
+            idx = [min(len(e_got) - 1, int(x * len(e_got))) for x in q]
+            print(f"S={S} n={n} det={det} peaked={peaked} pad={pad}: quantiles {q} kernel {[f'{e_got[i]:.2e}' for i in idx]} "
+                  f"reference fp32 {[f'{e_ref[i]:.2e}' for i in idx]}  worst ratio to 3x yardstick {ratio:.2f}")
+            assert ratio <= 1.0, (S, n, det, peaked, pad, ratio)
+    print(f"worst ratio {worst:.2f}")
+
+
+@pytest.mark.parametrize("S,n", [(32, 33), (128, 129)])
+def test_mip_resampler_error_vs_fp64_yardstick(ops, S, n):
+    """The same yardstick for sample_pdf (samplers.py:64-121)."""
+    N = 4096
+    for peaked in (False, True):
+        g, bins, w, *_ = _resample_inputs(N, S, 700 + S + int(peaked), peaked=peaked)
+        rand = torch.rand(N, n, generator=g)
+        for pad in (True, False):
+            ref32, _ = orc.sample_pdf(bins, w, n, pad, rand)
+            exact, _ = orc.sample_pdf(bins.double(), w.double(), n, pad, rand.double())
+            got = ops.sample_pdf(cu(bins), cu(w), n, pad, cu(rand)).cpu()
+            e_got, e_ref = _error_distributions(got, ref32, exact)
+            ratio = float(np.max(e_got / (3.0 * e_ref + 3 * 4.8e-7)))
+            print(f"mip S={S} peaked={peaked} pad={pad}: max kernel {e_got[-1]:.2e} reference fp32 {e_ref[-1]:.2e} ratio {ratio:.2f}")
+            assert ratio <= 1.0
+
+
 def test_dd_resampler_sorts_when_bins_leave_cfg_range(ops):
     """samplers.py:210-213: endpoints pinned to cfg near/far, then sorted -- exercised with a cfg range INSIDE the bins."""
     N, S, n = 19, 32, 33
@@ -223,6 +281,17 @@ def test_frame_to_u8_vs_oracle(ops, H, W):
     assert np.array_equal(disp8.cpu().numpy(), d_ref)
     assert np.array_equal(video.cpu().numpy(), orc.video_frame(rgb, d_ref))
     assert disp8.min().item() == 0 and disp8.max().item() == 255
+
+
+def test_frame_to_u8_reference_golden(ops):
+    """csrc/frame.cu against what the REFERENCE's cast_to_image / cast_to_disparity_image (visualization.py:11-27) and
+    its video-frame assembly (render_video.py:98-103) returned for the same float frame (tests/golden/frame_post.npz)."""
+    from ddnerf_b200.render import frame_to_u8
+    g = load_golden("frame_post")
+    rgb8, disp8, video = frame_to_u8(cu(g["rgb"]), cu(g["disp"]), want_video=True)
+    assert np.array_equal(np.moveaxis(rgb8.cpu().numpy(), -1, 0), g["rgb8_chw"].numpy())
+    assert np.array_equal(disp8.cpu().numpy()[None], g["disp8"].numpy())
+    assert np.array_equal(video.cpu().numpy(), g["video_bgr"].numpy())
 
 
 def test_frame_renderer_pose_to_u8(ops):

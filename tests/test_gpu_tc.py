@@ -495,3 +495,120 @@ def test_encode_img_vs_oracle(kind, N, S):
         err = (got - want).abs()
         assert (err <= 2.0 ** -8 * want.abs() + 3e-5).all(), err.max().item()
     assert (dirs[:, 27:] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 mode at the BENCHED configurations (BASELINE.json configs[1] and configs[2]), full size
+# ---------------------------------------------------------------------------------------------
+def _report(tag, got, ref, tol):
+    err = (got - ref).abs()
+    print(f"  {tag:18s} max {err.max().item():.3e}  mean {err.mean().item():.3e}  frac>{tol:g}: {(err > tol).float().mean().item():.2e}")
+    return err
+
+
+def test_bf16_cfg2_full_size_vs_oracle():
+    """BASELINE.json configs[1] as bench.py times it: config_blender_mipnerf, 4096 rays, 128 + 128 samples, train mode, bf16
+    tensor-core MLP -- against the fp32 oracle on the same weights / rays / random draws.  north_star's bf16 budget:
+    sample depths (the FINE fence-posts produced from the bf16 coarse pass), rendered rgb and depth within 5e-3 max-abs;
+    the loss within 5e-3; parameter-gradient direction against fp32 autograd."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    cfg, kind = preset("config_blender_mipnerf", num_coarse=128, num_fine=128)
+    N, s0, s1 = 4096, 128, 128
+    ro, rd, rad, near, far = synth_rays(kind, N, seed=3)
+    g = torch.Generator().manual_seed(0)
+    target = torch.rand(N, 3, generator=g)
+    rnd = dict(t_rand=torch.rand(N, s0 + 1, generator=g), noise0=torch.randn(N, s0, generator=g),
+               u_rand=torch.rand(N, s1 + 1, generator=g), noise1=torch.randn(N, s1, generator=g))
+    pc = orc.init_mlp_params(False, seed=7)
+    tp = cfg.train_params
+    ocfg = orc.PathConfig(model=cfg.nerf.type, near=near, far=far, num_coarse=s0, num_fine=s1, perturb=True,
+                          noise_std=cfg.nerf.train.radiance_field_noise_std, blender=True, pdf_padding=tp.pdf_padding,
+                          gaussian_smooth_factor=tp.gaussian_smooth_factor, dist_reg_coeficient=tp.dist_reg_coeficient,
+                          loss_coeficients=tp.loss_coeficients, dp_coeficient=tp.dp_coeficient)
+    rays = orc.pack_rays(ro, rd, rad, near, far)
+    loss_ref, out_ref, gc_ref, _ = orc.train_step(ocfg, pc, None, rays, target, rnd)
+
+    dev = torch.device("cuda:0")
+    model = M.GeneralMipNerfModel(cfg)
+    model.coarse.load_state_dict(pc)
+    model.coarse.mlp_mode = "bf16"
+    model.to(dev)
+    model.keep_t_vals = True
+    model.randoms = {k: v.to(dev) for k, v in rnd.items()}
+    tgt = target.to(dev)
+    out = model.run_iter(ro.to(dev), rd.to(dev), rad.to(dev), mode="train", rgb_target=tgt)
+    loss = sum(tp.loss_coeficients[j] * torch.nn.functional.mse_loss(out[j]["rgb"], tgt) for j in range(2))
+    loss.backward()
+    torch.cuda.synchronize()
+    print("cfg2 bf16 vs fp32 oracle (4096 rays x 128+128):")
+    for j in range(2):
+        t_got = torch.cat(model.last_t_vals[j]).cpu()
+        e_t = _report(f"pass {j} t_vals", t_got, out_ref[j]["t_vals"], 5e-3)
+        e_rgb = _report(f"pass {j} rgb", out[j]["rgb"].detach().cpu(), out_ref[j]["rgb"], 5e-3)
+        e_dep = _report(f"pass {j} depth", out[j]["depth"].detach().cpu(), out_ref[j]["depth"], 5e-3)
+        _report(f"pass {j} weights", out[j]["weights"].detach().cpu(), out_ref[j]["weights"], 5e-3)
+        assert e_t.max().item() < 5e-3 and e_rgb.max().item() < 5e-3 and e_dep.max().item() < 5e-3
+    assert abs(loss.item() - loss_ref.item()) < 5e-3
+    flat_got = torch.cat([p.grad.reshape(-1) for p in model.coarse.parameters()]).cpu().double()
+    flat_ref = torch.cat([gc_ref[k].reshape(-1) for k, _ in model.coarse.named_parameters()]).double()
+    cos = torch.nn.functional.cosine_similarity(flat_got, flat_ref, dim=0).item()
+    print(f"  whole-gradient cosine vs fp32 autograd: {cos:.5f}")
+    assert cos > 0.97
+
+
+def test_bf16_cfg3_ff_validation_slab_vs_oracle():
+    """BASELINE.json configs[2] as bench.py's render leg runs it: config_ff (DDNeRF, forward-facing NDC rays), validation mode
+    exactly as render_video.py:36-48 sets it up -- deterministic sampling, pdf_padding off, gaussian_smooth_factor =
+    final_smooth (1.1), noise std 1.0 (injected) -- on a 17-row slab of the 1008 x 756 frame (17,136 rays, one chunk of
+    16,384 + a ragged remainder), bf16 MLP, no_grad.  rgb / depth / disparity inputs and BOTH passes' sample depths within
+    5e-3 of the fp32 oracle (t in [0, 1])."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import full_frame_rays
+    cfg, kind = preset("config_ff")
+    cfg.train_params.pdf_padding = False
+    cfg.train_params.gaussian_smooth_factor = cfg.train_params.final_smooth
+    ro, rd, rad, near, far = full_frame_rays(kind)
+    r0, rows = 370, 17
+    ro, rd, rad = (t[r0:r0 + rows].contiguous() for t in (ro, rd, rad))
+    N = rows * ro.shape[1]
+    g = torch.Generator().manual_seed(2)
+    rnd = dict(noise0=torch.randn(N, 16, generator=g), noise1=torch.randn(N, 16, generator=g))
+    pc, pf = orc.init_mlp_params(True, seed=7), orc.init_mlp_params(False, seed=8)
+    tp = cfg.train_params
+    ocfg = orc.PathConfig(model="DDNerfModel", near=near, far=far, num_coarse=16, num_fine=16, perturb=False, noise_std=1.0,
+                          blender=False, pdf_padding=False, gaussian_smooth_factor=tp.final_smooth,
+                          dist_reg_coeficient=tp.dist_reg_coeficient)
+    with torch.no_grad():
+        ref = orc.predict_dd(ocfg, pc, pf, orc.pack_rays(ro, rd, rad, near, far), rnd)
+
+    dev = torch.device("cuda:0")
+    model = M.DDNerfModel(cfg)
+    model.coarse.load_state_dict(pc)
+    model.fine.load_state_dict(pf)
+    for net in (model.coarse, model.fine):
+        net.mlp_mode = "bf16"
+    model.to(dev)
+    model.eval()
+    model.record_distributions = False
+    model.keep_t_vals = True
+    model.randoms = {k: v.to(dev) for k, v in rnd.items()}
+    with torch.no_grad():
+        out = model.run_iter(ro.to(dev), rd.to(dev), rad.to(dev), mode="validation")
+    torch.cuda.synchronize()
+    assert out[1]["rgb"].shape == (rows, ro.shape[1], 3) and out[1]["disp"].shape == (rows, ro.shape[1])
+    print(f"cfg3 bf16 validation slab ({N} rays x 16+16) vs fp32 oracle:")
+    for j in range(2):
+        t_got = torch.cat(model.last_t_vals[j]).cpu()
+        e_t = _report(f"pass {j} t_vals", t_got, ref[j]["t_vals"], 5e-3)
+        e_rgb = _report(f"pass {j} rgb", out[j]["rgb"].reshape(-1, 3).cpu(), ref[j]["rgb"], 5e-3)
+        e_dep = _report(f"pass {j} depth", out[j]["depth"].reshape(-1).cpu(), ref[j]["depth"], 5e-3)
+        e_acc = _report(f"pass {j} acc", out[j]["acc"].reshape(-1).cpu(), ref[j]["acc"], 5e-3)
+        assert e_t.max().item() < 5e-3 and e_rgb.max().item() < 5e-3 and e_dep.max().item() < 5e-3 and e_acc.max().item() < 5e-3
+    e_cd = _report("corrected disp", out[0]["corrected_disp_map"].reshape(-1).cpu(), ref[0]["corrected_disp_map"], 5e-3)
+    rel = (e_cd / ref[0]["corrected_disp_map"].abs().clamp(min=1e-6)).max().item()
+    assert rel < 5e-3

@@ -199,3 +199,18 @@ def test_ray_bundle_restatement_golden():
     o, d, r = R.ndc_mipnerf_rays(H, W, focal, ro, rd, near=1)
     for got, key in ((o, "n_ro"), (d, "n_rd"), (r.squeeze(-1), "n_rad")):
         torch.testing.assert_close(got, g[key].reshape(got.shape), rtol=2e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# f4: frame post-processing against what the reference's own functions returned (tests/golden/frame_post.npz:
+# validation_utils/visualization.py:11-27 and the frame assembly of render_video.py:98-103, generated with
+# matplotlib / imageio stubbed -- make_golden.py: stage_frame)
+# ---------------------------------------------------------------------------------------------
+def test_frame_post_golden():
+    g = load_golden("frame_post")
+    rgb, disp = g["rgb"], g["disp"]
+    rgb8 = orc.cast_to_image(rgb)                                   # [H,W,3]
+    assert np.array_equal(np.moveaxis(rgb8, -1, 0), g["rgb8_chw"].numpy())
+    d8 = orc.cast_to_disparity_image(disp)                           # [H,W]
+    assert np.array_equal(d8[None], g["disp8"].numpy())
+    assert np.array_equal(orc.video_frame(rgb, d8), g["video_bgr"].numpy())
