@@ -551,8 +551,8 @@ def main():
 
     def step_store(s):
         loss, mse = trainer.step(*store.get_training_rays_for_next_iter(n_rays, dev))
-        loss_host[0:1].copy_(loss.reshape(1), non_blocking=True)
-        loss_host[1:3].copy_(mse, non_blocking=True)
+        loss_host[0, 0:1].copy_(loss.reshape(1), non_blocking=True)
+        loss_host[0, 1:3].copy_(mse, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for s in range(2):

@@ -62,6 +62,10 @@ SIGNATURES = {
     "ddnerf_tc_mma_rate": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p]),
     "ddnerf_composite_forward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 7 + [c_l, c_i, c_p]),
     "ddnerf_composite_backward": (c_i, [c_p, c_i, c_p, c_p, c_l, c_p, c_f, c_p, c_i, c_i] + [c_p] * 8 + [c_l, c_i, c_p]),
+    "ddnerf_sample_pdf_mu_sigma_fused": (c_i, [c_p] * 4 + [c_f] + [c_p] * 4 + [c_l, c_i, c_i, c_i, c_f, c_f, c_p]),
+    "ddnerf_composite_dd_scratch_floats": (c_l, [c_l]),
+    "ddnerf_composite_dd_forward": (c_i, [c_p, c_p, c_p, c_l, c_p, c_f, c_i, c_i, c_f] + [c_p] * 10 + [c_l, c_i, c_p]),
+    "ddnerf_composite_dd_backward": (c_i, [c_p, c_p, c_p, c_l, c_p, c_f, c_i, c_i, c_f] + [c_p] * 10 + [c_l, c_i, c_p]),
     "ddnerf_dp_loss_forward": (c_i, [c_p] * 8 + [c_i, c_p, c_p, c_l, c_i, c_i, c_p]),
     "ddnerf_dp_loss_backward": (c_i, [c_p] * 8 + [c_i] + [c_p] * 5 + [c_l, c_i, c_i, c_p]),
     "ddnerf_mse_loss": (c_i, [c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_p]),

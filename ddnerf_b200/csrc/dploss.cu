@@ -28,6 +28,14 @@ struct DpArgs {
 
 __device__ __forceinline__ float warp_sum32(float v) { return group_sum<32>(v); }
 
+// left_tail / part_inside of coarse cell (models.py:254-258, detached constants of the loss): read from the caller's
+// tensors, or -- fused DDNeRF coarse path, both pointers NULL -- evaluated per cell with the reference's fp32 formula.
+__device__ __forceinline__ void cell_tails(const DpArgs& a, int64_t off, float mu, float sigma, float& lt, float& pin) {
+    if (a.lt0) { lt = __ldg(a.lt0 + off); pin = __ldg(a.pin0 + off); return; }
+    lt = normal_cdff_((0.0f - mu) / sigma);
+    pin = normal_cdff_((1.0f - mu) / sigma) - lt;
+}
+
 // #{m in [0,len): v[m] < x}
 __device__ __forceinline__ int count_lt(const float* v, int len, float x) {
     int lo = 0, hi = len;
@@ -58,10 +66,13 @@ __device__ __forceinline__ Edge eval_edge(const DpArgs& a, const Smem& sm, int64
     while (j > 0 && sm.cdf[j - 1] == sm.cdf[j]) --j;          // torch.max: first index of the maximum
     e.idx = j;
     e.width = sm.t0s[j + 1] - sm.t0s[j];
-    float mur = sm.t0s[j] + __ldg(a.mus0 + ray * a.S0 + j) * e.width;
-    e.sr = __ldg(a.sig0 + ray * a.S0 + j) * e.width;
+    const float mu_j = __ldg(a.mus0 + ray * a.S0 + j), sg_j = __ldg(a.sig0 + ray * a.S0 + j);
+    float mur = sm.t0s[j] + mu_j * e.width;
+    e.sr = sg_j * e.width;
     e.x = (t1k - mur) / e.sr;
-    e.F = (normal_cdff_(e.x) - __ldg(a.lt0 + ray * a.S0 + j)) / __ldg(a.pin0 + ray * a.S0 + j);
+    float lt_j, pin_j;
+    cell_tails(a, ray * a.S0 + j, mu_j, sg_j, lt_j, pin_j);
+    e.F = (normal_cdff_(e.x) - lt_j) / pin_j;
     e.eraw = sm.cdf[j] + e.F * sm.p0[j];
     return e;
 }
@@ -177,7 +188,8 @@ __global__ void dp_loss_bwd_kernel(DpArgs a, const float* __restrict__ g_loss, c
         const int j = e.idx;
         atomicAdd(gcdf + j, gE);
         atomicAdd(gp0 + j, gE * e.F);
-        float pin = __ldg(a.pin0 + ray * S0 + j);
+        float lt_unused, pin;
+        cell_tails(a, ray * S0 + j, __ldg(a.mus0 + ray * S0 + j), __ldg(a.sig0 + ray * S0 + j), lt_unused, pin);
         float gx = gE * sm.p0[j] / pin * (0.3989422804f * expf(-0.5f * e.x * e.x));
         atomicAdd(gmu + j, -gx / e.sr * e.width);
         atomicAdd(gsg + j, -gx * e.x / e.sr * e.width);
@@ -300,7 +312,11 @@ struct CellDp {
             const int q = min(gl + c * G, S0 - 1);
             t0n[c] = __ldg(t0r + q + 1);
             muv[c] = __ldg(a.mus0 + r0 + q); sgv[c] = __ldg(a.sig0 + r0 + q);
-            ltv[c] = __ldg(a.lt0 + r0 + q); piv[c] = __ldg(a.pin0 + r0 + q);
+            if (a.lt0) { ltv[c] = __ldg(a.lt0 + r0 + q); piv[c] = __ldg(a.pin0 + r0 + q); }
+        }
+        if (!a.lt0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) cell_tails(a, 0, muv[c], sgv[c], ltv[c], piv[c]);
         }
         // ---- fine-side normalisers ----
         float p1 = 0.f, raw1 = 0.f;
@@ -555,8 +571,8 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float
                                       const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
                                       int blender, float* loss_out, float* scratch, int64_t N, int S0, int S1,
                                       void* stream) {
-    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && lt0 && pin0 && loss_out && scratch,
-                     "dp_loss_forward: null pointer");
+    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && loss_out && scratch, "dp_loss_forward: null pointer");
+    DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_forward: lt0 and pin0 go together (both NULL: computed in the kernel)");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_forward: S0=%d S1=%d unsupported", S0, S1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st);
@@ -589,8 +605,9 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const floa
                                        const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
                                        int blender, const float* g_loss, const float* scratch, float* g_w0,
                                        float* g_mus0, float* g_sigmas0, int64_t N, int S0, int S1, void* stream) {
-    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && lt0 && pin0 && g_loss && scratch && g_w0 && g_mus0 &&
-                         g_sigmas0, "dp_loss_backward: null pointer");
+    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && g_loss && scratch && g_w0 && g_mus0 && g_sigmas0,
+                     "dp_loss_backward: null pointer");
+    DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_backward: lt0 and pin0 go together");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_backward: S0=%d S1=%d unsupported", S0, S1);
     if (N == 0) return 0;
     DpArgs a{t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, N, S0, S1};

@@ -308,6 +308,18 @@ __global__ void __launch_bounds__(256) sample_pdf_fast_kernel(const float* __res
     }
 }
 
+// Fused DDNeRF coarse path: part_inside / left_tail are NULL and `sigmas` holds the UNSMOOTHED sigmas; the kernel applies
+// gaussian_smooth_factor (a kernel argument, or read from device memory when the step is a replayed CUDA graph) and
+// evaluates the two tails per cell with the reference's own fp32 formula, models.py:268-273 / math_utils.py:193-200:
+// {part_inside, left_tail, smoothed sigma, mu}.
+struct Smooth { float value; const float* dev; };
+__device__ __forceinline__ float4 dd_cell(float mu, float sigma, float smooth) {
+    const float ss = sigma * smooth;
+    const float lt = normal_cdff_((0.0f - mu) / ss);
+    const float pin = normal_cdff_((1.0f - mu) / ss) - lt;
+    return make_float4(pin, lt, ss, mu);
+}
+
 // DDNeRF variant.  The per-cell Gaussian parameters (part_inside, left_tail, sigma, mu) are staged in shared
 // memory next to the {cdf, bin} pairs -- gathered from global memory they put one DRAM latency into every
 // output chunk.  Dynamic shared memory per ray: P float4 + (P+1) float2 (rounded to 16 bytes).
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
     const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ mus,
     const float* __restrict__ sigmas, const float* __restrict__ part_inside, const float* __restrict__ left_tail,
     const float* __restrict__ rand, float* __restrict__ out, int32_t* __restrict__ idx_out, int64_t N, int S, int n,
-    int pdf_padding, float near_cfg, float far_cfg, USpec us) {
+    int pdf_padding, float near_cfg, float far_cfg, USpec us, Smooth smooth) {
     using F = FastCdf<G, C>;
     extern __shared__ float4 dd_smem[];
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
@@ -334,13 +346,25 @@ __global__ void __launch_bounds__(256) sample_pdf_mu_sigma_fast_kernel(
     {
         const float* mu_r = mus + ray * S;
         const float* sg_r = sigmas + ray * S;
-        const float* pin_r = part_inside + ray * S;
-        const float* lt_r = left_tail + ray * S;
         float4 pv[C];
+        if (part_inside) {
+            const float* pin_r = part_inside + ray * S;
+            const float* lt_r = left_tail + ray * S;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int q = min(gl + c * G, S - 1);
-            pv[c] = make_float4(__ldg(pin_r + q), __ldg(lt_r + q), __ldg(sg_r + q), __ldg(mu_r + q));
+            for (int c = 0; c < C; ++c) {
+                const int q = min(gl + c * G, S - 1);
+                pv[c] = make_float4(__ldg(pin_r + q), __ldg(lt_r + q), __ldg(sg_r + q), __ldg(mu_r + q));
+            }
+        } else {
+            const float sm = smooth.dev ? __ldg(smooth.dev) : smooth.value;
+            float mv[C], sv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int q = min(gl + c * G, S - 1);
+                mv[c] = __ldg(mu_r + q); sv[c] = __ldg(sg_r + q);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) pv[c] = dd_cell(mv[c], sv[c], sm);
         }
         F::build(weights + ray * S, bins + ray * (S + 1), cb, S, gl, pdf_padding);   // ends with __syncwarp
 #pragma unroll
@@ -465,11 +489,13 @@ __global__ void sample_pdf_mu_sigma_kernel(const float* __restrict__ bins, const
                                            const float* __restrict__ rand, float* __restrict__ out,
                                            int32_t* __restrict__ idx_out, int64_t N, int S, int n, int n_pow2,
                                            int pdf_padding, float near_cfg, float far_cfg, USpec us,
-                                           int per_warp_floats) {
+                                           int per_warp_floats, Smooth smooth) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= N) return;
+    const bool fused = part_inside == nullptr;
+    const float smf = fused ? (smooth.dev ? __ldg(smooth.dev) : smooth.value) : 1.0f;
     float* wpad = smem + (size_t)warp * per_warp_floats;
     float* what = wpad + (S + 2);
     float* cdf = what + S;
@@ -479,17 +505,23 @@ __global__ void sample_pdf_mu_sigma_kernel(const float* __restrict__ bins, const
     build_cdf(weights + ray * S, wpad, what, cdf, S, lane, pdf_padding);
     const float* mu_r = mus + ray * S;
     const float* sg_r = sigmas + ray * S;
-    const float* pin_r = part_inside + ray * S;
-    const float* lt_r = left_tail + ray * S;
+    const float* pin_r = fused ? nullptr : part_inside + ray * S;
+    const float* lt_r = fused ? nullptr : left_tail + ray * S;
+    auto cell = [&](int q) {                                             // {part_inside, left_tail, sigma, mu} of cell q
+        return fused ? dd_cell(__ldg(mu_r + q), __ldg(sg_r + q), smf)
+                     : make_float4(__ldg(pin_r + q), __ldg(lt_r + q), __ldg(sg_r + q), __ldg(mu_r + q));
+    };
     for (int k = lane; k < n_pow2; k += 32) {
         float val = __int_as_float(0x7f800000);                          // +inf padding for the sort
         if (k < n) {
             float u = make_u(us, k, n, rand ? rand + ray * n : nullptr);
             float z, b0, b1;
             int ind;
+            float4 pp;
             if (S == 1) {                                                // samplers.py:185-190
                 ind = 0; b0 = sb[0]; b1 = sb[1];
-                z = u * __ldg(pin_r) + __ldg(lt_r);
+                pp = cell(0);
+                z = u * pp.x + pp.y;
             } else {
                 int j = max(count_le(cdf, S + 1, u) - 1, 0);
                 int j1 = min(j + 1, S);
@@ -498,11 +530,12 @@ __global__ void sample_pdf_mu_sigma_kernel(const float* __restrict__ bins, const
                 ind = j;                                                 // torch.max: first index of the maximum
                 while (ind > 0 && sb[ind - 1] == sb[ind]) --ind;
                 ind = min(ind, S - 1);
-                z = ((u - c0) / (c1 - c0)) * __ldg(pin_r + ind) + __ldg(lt_r + ind);
+                pp = cell(ind);
+                z = ((u - c0) / (c1 - c0)) * pp.x + pp.y;
                 z = fminf(z, 0.999f);
             }
             z = 1.41421354f * erfinvf(2.0f * z - 1.0f);                  // math_utils.py:202-208
-            float t = fminf(fmaxf(z * __ldg(sg_r + ind) + __ldg(mu_r + ind), 0.f), 0.99999f);
+            float t = fminf(fmaxf(z * pp.z + pp.w, 0.f), 0.99999f);
             val = b0 + t * (b1 - b0);
             if (k == 0) val = near_cfg;                                  // samplers.py:210-211
             if (k == n - 1) val = far_cfg;
@@ -593,12 +626,10 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf(const float* bins, const float* w
     return 0;
 }
 
-extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const float* weights, const float* mus, const float* sigmas,
-                                          const float* part_inside, const float* left_tail, const float* rand, float* out,
-                                          int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, float near_cfg,
-                                          float far_cfg, void* stream) {
-    DDNERF_CHECK_ARG(bins && weights && mus && sigmas && part_inside && left_tail && out,
-                     "sample_pdf_mu_sigma: null pointer");
+static int sample_dd_impl(const float* bins, const float* weights, const float* mus, const float* sigmas,
+                          const float* part_inside, const float* left_tail, Smooth smooth, const float* rand, float* out,
+                          int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, float near_cfg, float far_cfg,
+                          void* stream) {
     DDNERF_CHECK_ARG(S >= 1 && S <= 2048 && n >= 2 && n <= 4096, "sample_pdf_mu_sigma: S=%d n=%d unsupported", S, n);
     if (N == 0) return 0;
     double s = 1.0 / (n - 1);
@@ -610,7 +641,7 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const
         constexpr int bytes = (256 / G) * dd_ray_smem_bytes<G, C>();
         if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         kern<<<ceil_div(N, 256 / G), 256, bytes, st>>>(bins, weights, mus, sigmas, part_inside, left_tail, rand, out,
-                                                       idx_out, N, S, n, pdf_padding, near_cfg, far_cfg, us);
+                                                       idx_out, N, S, n, pdf_padding, near_cfg, far_cfg, us, smooth);
     });
     if (!fast) {
         int np2 = next_pow2(n);
@@ -619,10 +650,30 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const
         DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf_mu_sigma: S=%d n=%d needs too much shared memory", S, n);
         sample_pdf_mu_sigma_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(
             bins, weights, mus, sigmas, part_inside, left_tail, rand, out, idx_out, N, S, n, np2, pdf_padding, near_cfg,
-            far_cfg, us, per_warp);
+            far_cfg, us, per_warp, smooth);
     }
     DDNERF_LAUNCHED("sample_pdf_mu_sigma", 1);
     return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const float* weights, const float* mus, const float* sigmas,
+                                          const float* part_inside, const float* left_tail, const float* rand, float* out,
+                                          int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, float near_cfg,
+                                          float far_cfg, void* stream) {
+    DDNERF_CHECK_ARG(bins && weights && mus && sigmas && part_inside && left_tail && out,
+                     "sample_pdf_mu_sigma: null pointer");
+    return sample_dd_impl(bins, weights, mus, sigmas, part_inside, left_tail, Smooth{1.0f, nullptr}, rand, out, idx_out, N, S,
+                          n, pdf_padding, near_cfg, far_cfg, stream);
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma_fused(const float* bins, const float* weights, const float* mus,
+                                                const float* sigmas, float smooth, const float* smooth_dev,
+                                                const float* rand, float* out, int32_t* idx_out, int64_t N, int S, int n,
+                                                int pdf_padding, float near_cfg, float far_cfg, void* stream) {
+    DDNERF_CHECK_ARG(bins && weights && mus && sigmas && out, "sample_pdf_mu_sigma_fused: null pointer");
+    DDNERF_CHECK_ARG(smooth_dev || smooth > 0.f, "sample_pdf_mu_sigma_fused: gaussian_smooth_factor=%g must be positive", smooth);
+    return sample_dd_impl(bins, weights, mus, sigmas, nullptr, nullptr, Smooth{smooth, smooth_dev}, rand, out, idx_out, N, S, n,
+                          pdf_padding, near_cfg, far_cfg, stream);
 }
 
 extern "C" DDNERF_EXPORT int ddnerf_find_interval(const float* cdf, const float* u, int32_t* idx_out, int64_t N, int S, int n,

@@ -15,7 +15,8 @@ from . import base_architectures
 from .samplers import *  # noqa: F401,F403
 from .samplers import sample_first_cycle, sample_pdf, sample_pdf_with_mu_sigma
 from .dd_utils import estimate_dp_loss
-from ..general_utils.volume_rendering_utils import volume_render_radiance_field
+from ..general_utils.volume_rendering_utils import volume_render_radiance_field, _is_blender
+from .. import ops
 from ..general_utils.nerf_helpers import get_embedding_function, get_minibatches
 from ..general_utils.math_utils import approximate_cdf, integrated_pos_enc
 
@@ -171,47 +172,45 @@ class DDNerfModel(GeneralMipNerfModel):
         tp = self.cfg.train_params
         ret = {}
 
-        # ---- pass 0: coarse network with the depth-distribution head (models.py:222-273)
+        # ---- pass 0: coarse network with the depth-distribution head (models.py:222-273).  Everything after the
+        # network -- sigmoid of the (mu, sigma) head, regulariser sums, compositing with the corrected depth -- is ONE
+        # kernel (ops.composite_dd); the tails Phi((0-mu)/sigma), Phi((1-mu)/sigma) and their smoothed versions are
+        # evaluated per cell inside the resampler / dp-loss kernels that consume them.
         t0 = sample_first_cycle(self.cfg, near, far, mode, t_rand=self._rnd("t_rand"))
         rf0 = self.run_network(ray_batch, t0, self.coarse, mode)
-        raw_mus, raw_sigmas = rf0[:, :, -2], rf0[:, :, -1]
-        mus = torch.sigmoid(raw_mus)
-        sigmas = torch.sigmoid(raw_sigmas) + 0.001
-        sig_loss = (torch.abs(raw_sigmas) ** 2).sum() / raw_sigmas.shape[0]
-        mus_loss = (torch.abs(raw_mus) ** 2).sum() / raw_mus.shape[0]
-        mus_reg = tp.dist_reg_coeficient * mus_loss
-        sig_reg = tp.dist_reg_coeficient * sig_loss
-        left_tail = approximate_cdf((0 - mus) / sigmas)
-        part_inside = approximate_cdf((1 - mus) / sigmas) - left_tail
-        rgb, disp, acc, w0, depth, cdisp, _ = volume_render_radiance_field(
-            rf0[:, :, :-2], t0, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
-            white_background=mcfg.white_background, mus=mus, cfg=self.cfg, noise=self._rnd("noise0"), want_rgb=False)
-        smoothed_sigmas = sigmas * tp.gaussian_smooth_factor
-        smoothed_left_tail = approximate_cdf((0 - mus) / smoothed_sigmas)
-        smoothed_part_inside = approximate_cdf((1 - mus) / smoothed_sigmas) - smoothed_left_tail
-        rec = {}
+        noise0 = self._rnd("noise0")
+        std = mcfg.radiance_field_noise_std
+        if std > 0.0 and noise0 is None:
+            noise0 = torch.randn(rf0.shape[:2], dtype=rf0.dtype, device=rf0.device)      # volume_rendering_utils.py:31
+        rgb, disp, acc, w0, depth, cdisp, mus, sigmas, regs = ops.composite_dd(
+            rf0, t0, rd, noise0 if std > 0.0 else None, std, mcfg.white_background, _is_blender(self.cfg),
+            tp.dist_reg_coeficient)
+        mus_loss, sig_loss, mus_reg, sig_reg = regs[0:1], regs[1:2], regs[2:3], regs[3:4]
         if self.record_distributions:                           # models.py:292-300 (mask from pass 0)
+            smoothed_sigmas = sigmas * tp.gaussian_smooth_factor
             sel = (w0 / torch.sum(w0, dim=-1, keepdim=True)) > 0.1
             rec = {"mus": mus[sel], "sigmas": sigmas[sel], "smoothed_sigmas": smoothed_sigmas[sel]}
         else:
             rec = {"mus": None, "sigmas": None, "smoothed_sigmas": None}
         ret[0] = {"rgb": rgb, "disp": disp, "acc": acc, "weights": w0, "depth": depth, **rec, "dp_loss": None,
-                  "corrected_disp_map": cdisp, "mus_loss": mus_loss.unsqueeze(0), "sig_loss": sig_loss.unsqueeze(0),
-                  "mus_reg": mus_reg.unsqueeze(0), "sig_reg": sig_reg.unsqueeze(0)}
+                  "corrected_disp_map": cdisp, "mus_loss": mus_loss, "sig_loss": sig_loss, "mus_reg": mus_reg,
+                  "sig_reg": sig_reg}
 
         # ---- pass 1: fine network on depth-distribution samples (models.py:225-237, 276-289)
-        t1 = sample_pdf_with_mu_sigma(t0, w0, mus, smoothed_sigmas, smoothed_part_inside, smoothed_left_tail,
-                                      mcfg.num_fine + 1, self.cfg, det=(mcfg.perturb == 0.0),
-                                      rand=self._rnd("u_rand")).detach()
+        det = mcfg.perturb == 0.0
+        u_rand = None if det else self._rnd("u_rand")
+        if not det and u_rand is None:
+            u_rand = torch.rand(w0.shape[0], mcfg.num_fine + 1, device=w0.device)          # samplers.py:165
+        t1 = ops.sample_pdf_mu_sigma_fused(t0, w0, mus, sigmas, tp.gaussian_smooth_factor, mcfg.num_fine + 1,
+                                           tp.pdf_padding, self.cfg.dataset.near, self.cfg.dataset.far, u_rand)
         self._record_t(0, t0)
         self._record_t(1, t1)
         rf1 = self.run_network(ray_batch, t1, self.fine, mode)
         rgb1, disp1, acc1, w1, depth1, _, _ = volume_render_radiance_field(
             rf1, t1, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
             white_background=mcfg.white_background, mus=None, cfg=self.cfg, noise=self._rnd("noise1"), want_rgb=False)
-        dp_loss = estimate_dp_loss(t1, t0, w1.detach(), w0, mus, sigmas, left_tail.detach(), part_inside.detach(),
-                                   self.cfg) * (t1.shape[1] - 1)
-        dp_loss = (dp_loss + mus_reg + sig_reg).unsqueeze(0)
+        dp_loss = estimate_dp_loss(t1, t0, w1.detach(), w0, mus, sigmas, None, None, self.cfg) * (t1.shape[1] - 1)
+        dp_loss = dp_loss + mus_reg + sig_reg                    # [1] (mus_reg / sig_reg are [1] views of regs)
         ret[1] = {"rgb": rgb1, "disp": disp1, "acc": acc1, "weights": w1, "depth": depth1, **rec, "dp_loss": dp_loss,
                   "corrected_disp_map": None}
         return ret

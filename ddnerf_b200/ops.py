@@ -98,6 +98,28 @@ def sample_pdf_mu_sigma(bins, weights, mus, sigmas, part_inside, left_tail, num_
     return (out, idx) if return_idx else out
 
 
+def sample_pdf_mu_sigma_fused(bins, weights, mus, sigmas, smooth, num_samples, pdf_padding, near_cfg, far_cfg, rand=None):
+    """sample_pdf_with_mu_sigma fed with the UNSMOOTHED sigmas: the kernel applies ``smooth`` (gaussian_smooth_factor; a
+    python float, or a 0-dim CUDA tensor when the step is a replayed CUDA graph) and evaluates the smoothed tails of
+    models.py:268-273 per cell."""
+    lib = _lib.load()
+    bins, weights = _req(bins, "bins"), _req(weights.detach(), "weights")
+    mus, sigmas = _req(mus.detach(), "mus"), _req(sigmas.detach(), "sigmas")
+    rand = _opt(rand, "rand")
+    N, S = weights.shape
+    out = torch.empty(N, num_samples, device=bins.device, dtype=torch.float32)
+    if isinstance(smooth, torch.Tensor):
+        if not (smooth.is_cuda and smooth.dtype == torch.float32):
+            raise RuntimeError("ddnerf_b200: a tensor gaussian_smooth_factor must be a fp32 CUDA scalar")
+        sm_val, sm_dev = 0.0, _p(smooth)
+    else:
+        sm_val, sm_dev = float(smooth), None
+    _lib.check(lib.ddnerf_sample_pdf_mu_sigma_fused(_p(bins), _p(weights), _p(mus), _p(sigmas), sm_val, sm_dev, _p(rand),
+                                                    _p(out), None, N, S, num_samples, int(bool(pdf_padding)), float(near_cfg),
+                                                    float(far_cfg), _stream()), "sample_pdf_mu_sigma_fused")
+    return out
+
+
 def find_interval(cdf, u):
     """idx[r,k] = #{cdf[r,:] <= u[r,k]} - 1 (int32), the interval search of samplers.py:106-116."""
     lib = _lib.load()
@@ -265,6 +287,58 @@ def composite(raw, t_vals, rd, noise=None, noise_std=0.0, mus=None, white_backgr
     return _Composite.apply(raw, t_vals, rd, noise, noise_std, mus, white_background, blender, want_rgb)
 
 
+class _CompositeDD(torch.autograd.Function):
+    """The coarse pass of DDNerfModel.predict after the network (models.py:242-273) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, raw6, t_vals, rd, noise, noise_std, white_background, blender, dist_reg_coef):
+        lib = _lib.load()
+        raw6 = _req(raw6, "radiance_field")
+        if raw6.dim() != 3 or raw6.shape[2] != 6:
+            raise RuntimeError("ddnerf_b200: composite_dd needs the [N,S,6] output of the DDNeRF coarse network")
+        N, S = raw6.shape[0], raw6.shape[1]
+        t_vals = _req(t_vals, "depth_values")
+        if not (rd.is_cuda and rd.dtype == torch.float32 and rd.dim() == 2 and rd.stride(1) == 1):
+            rd = _req(rd, "ray_directions")
+        noise = _opt(noise, "noise")
+        dev = raw6.device
+        rgb_map = torch.empty(N, 3, device=dev)
+        disp, acc, depth, cdisp = (torch.empty(N, device=dev) for _ in range(4))
+        weights, mus, sigmas = (torch.empty(N, S, device=dev) for _ in range(3))
+        regs = torch.empty(4, device=dev)
+        scratch = torch.empty(lib.ddnerf_composite_dd_scratch_floats(N), device=dev)
+        _lib.check(lib.ddnerf_composite_dd_forward(_p(raw6), _p(t_vals), _p(rd), rd.stride(0) if N > 1 else 3, _p(noise),
+                                                   float(noise_std), int(bool(white_background)), int(bool(blender)),
+                                                   float(dist_reg_coef), _p(rgb_map), _p(disp), _p(acc), _p(weights), _p(depth),
+                                                   _p(cdisp), _p(mus), _p(sigmas), _p(regs), _p(scratch), N, S, _stream()),
+                   "composite_dd_forward")
+        ctx.save_for_backward(raw6, t_vals, rd, noise)
+        ctx.cfg = (float(noise_std), bool(white_background), bool(blender), float(dist_reg_coef), N, S)
+        ctx.set_materialize_grads(False)
+        return rgb_map, disp, acc, weights, depth, cdisp, mus, sigmas, regs
+
+    @staticmethod
+    def backward(ctx, g_rgb_map, g_disp, g_acc, g_weights, g_depth, g_cdisp, g_mus, g_sigmas, g_regs):
+        lib = _lib.load()
+        raw6, t_vals, rd, noise = ctx.saved_tensors
+        noise_std, white, blender, coef, N, S = ctx.cfg
+        gs = [None if g is None else g.contiguous().float()
+              for g in (g_rgb_map, g_disp, g_acc, g_weights, g_depth, g_cdisp, g_mus, g_sigmas, g_regs)]
+        if all(g is None for g in gs):
+            return (None,) * 8
+        g_raw6 = torch.empty(N, S, 6, device=raw6.device, dtype=torch.float32)
+        _lib.check(lib.ddnerf_composite_dd_backward(_p(raw6), _p(t_vals), _p(rd), rd.stride(0) if N > 1 else 3, _p(noise),
+                                                    noise_std, int(white), int(blender), coef, *[_p(g) for g in gs],
+                                                    _p(g_raw6), N, S, _stream()), "composite_dd_backward")
+        return g_raw6, None, None, None, None, None, None, None
+
+
+def composite_dd(raw6, t_vals, rd, noise=None, noise_std=0.0, white_background=False, blender=False, dist_reg_coef=0.0):
+    """Returns (rgb_map, disp, acc, weights, depth [corrected], corrected_disp, mus, sigmas, regs[4]) with
+    regs = [mus_loss, sig_loss, mus_reg, sig_reg] (models.py:242-264).  Gradients flow to raw6 from every output."""
+    return _CompositeDD.apply(raw6, t_vals, rd, noise, noise_std, white_background, blender, dist_reg_coef)
+
+
 # ---------------------------------------------------------------------------------------------
 # K5 depth-distribution loss
 # ---------------------------------------------------------------------------------------------
@@ -273,7 +347,10 @@ class _DpLoss(torch.autograd.Function):
     def forward(ctx, t1, t0, w1, w0, mus0, sig0, lt0, pin0, blender):
         lib = _lib.load()
         t1, t0, w1, w0 = _req(t1, "t_vals_1"), _req(t0, "t_vals_0"), _req(w1, "pdf_1"), _req(w0, "pdf_0")
-        mus0, sig0, lt0, pin0 = _req(mus0, "mus_0"), _req(sig0, "sigmas_0"), _req(lt0, "left_tails_0"), _req(pin0, "part_inside")
+        mus0, sig0 = _req(mus0, "mus_0"), _req(sig0, "sigmas_0")
+        if (lt0 is None) != (pin0 is None):
+            raise RuntimeError("ddnerf_b200: dp_loss takes left_tails_0 and part_inside_0 together (both None: computed in the kernel)")
+        lt0, pin0 = _opt(lt0, "left_tails_0"), _opt(pin0, "part_inside")
         N, S0, S1 = w0.shape[0], w0.shape[1], w1.shape[1]
         loss = torch.empty((), device=w0.device, dtype=torch.float32)
         scratch = torch.empty(4 + 2 * N, device=w0.device, dtype=torch.float32)      # header + per-ray KL and relevance
@@ -297,7 +374,8 @@ class _DpLoss(torch.autograd.Function):
 
 
 def dp_loss(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender):
-    """kl_div(log q, p1, 'mean') of dd_utils.py:6-78.  Gradients flow to pdf_0, mus_0, sigmas_0."""
+    """kl_div(log q, p1, 'mean') of dd_utils.py:6-78.  Gradients flow to pdf_0, mus_0, sigmas_0.  With
+    left_tails_0 = part_inside_0 = None the kernels evaluate the two tails themselves (models.py:254-258)."""
     return _DpLoss.apply(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender)
 
 

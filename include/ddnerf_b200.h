@@ -52,6 +52,14 @@ int ddnerf_sample_pdf_mu_sigma(const float* bins, const float* weights, const fl
                                int32_t* idx_out, int64_t N, int S, int n, int pdf_padding,
                                float near_cfg, float far_cfg, void* stream);
 
+/* The same resampler fed by ddnerf_composite_dd_forward: `sigmas` are the UNSMOOTHED sigmas; the kernel multiplies by
+ * gaussian_smooth_factor (`smooth`, or *smooth_dev when non-NULL: a replayed CUDA graph reads the annealed factor from
+ * device memory) and evaluates smoothed_left_tail / smoothed_part_inside (models/models.py:268-273) per cell. */
+int ddnerf_sample_pdf_mu_sigma_fused(const float* bins, const float* weights, const float* mus,
+                                     const float* sigmas, float smooth, const float* smooth_dev,
+                                     const float* rand, float* out, int32_t* idx_out, int64_t N, int S,
+                                     int n, int pdf_padding, float near_cfg, float far_cfg, void* stream);
+
 /* The interval search alone (samplers.py:106-116): idx = #{cdf <= u} - 1, on caller-provided
  * CDFs.  Used by the bit-exactness test ("identical CDFs -> identical indices"). */
 int ddnerf_find_interval(const float* cdf, const float* u, int32_t* idx_out, int64_t N,
@@ -219,11 +227,37 @@ int ddnerf_raystore_gather(const float* rows, int64_t total_rows, const int64_t*
                            float* ray_origins, float* ray_directions, float* radii, float* target_rgb,
                            int* bad_index_flag, void* stream);
 
+/* ---- K4 + DDNeRF depth-distribution head (the coarse pass of DDNerfModel.predict, models/models.py:242-273) ----------
+ * The compositor above with the glue around it folded in.  raw6 [N,S,6] = (r,g,b,density,raw_mu,raw_sigma), read in
+ * place.  Writes the compositor outputs (depth = the corrected depth, volume_rendering_utils.py:76-83) plus
+ *   mus = sigmoid(raw_mu) [N,S], sigmas = sigmoid(raw_sigma) + 0.001 [N,S]                       (models.py:245-246)
+ *   regs[4] = {mus_loss, sig_loss, mus_reg, sig_reg} = {sum raw_mu^2 / N, sum raw_sigma^2 / N, dist_reg_coef x each}
+ *                                                                                             (models.py:248-252)
+ * The tails of models.py:254-258 / 268-273 are computed by their consumers (ddnerf_sample_pdf_mu_sigma_fused,
+ * ddnerf_dp_loss_* with NULL tails).  scratch: ddnerf_composite_dd_scratch_floats(N) floats, contents irrelevant. */
+int64_t ddnerf_composite_dd_scratch_floats(int64_t N);
+int ddnerf_composite_dd_forward(const float* raw6, const float* t, const float* rd, int64_t rd_stride,
+                                const float* noise, float noise_std, int white_background, int blender,
+                                float dist_reg_coef, float* rgb_map, float* disp, float* acc,
+                                float* weights, float* depth, float* cdisp, float* mus, float* sigmas,
+                                float* regs, float* scratch, int64_t N, int S, void* stream);
+/* Cotangents (each may be NULL) of the maps, the weights, mus, sigmas and regs[4] -> g_raw6 [N,S,6], the cotangent of the
+ * network output (sigmoid' of the mu/sigma head and the regulariser gradients 2 raw / N included). */
+int ddnerf_composite_dd_backward(const float* raw6, const float* t, const float* rd, int64_t rd_stride,
+                                 const float* noise, float noise_std, int white_background, int blender,
+                                 float dist_reg_coef, const float* g_rgb_map, const float* g_disp,
+                                 const float* g_acc, const float* g_weights, const float* g_depth,
+                                 const float* g_cdisp, const float* g_mus, const float* g_sigmas,
+                                 const float* g_regs, float* g_raw6, int64_t N, int S, void* stream);
+
 /* ---- K5: depth-distribution loss (models/dd_utils.py:6-78) ------------------------------- */
 /* scratch: >= 4 + 2*N floats of caller-owned workspace: [0] = sum of the per-ray KL values, [1] = number of
  * rays kept by the blender row filter (dd_utils.py:12-28), [4 .. 4+N) per-ray KL, [4+N .. 4+2N) per-ray kept
  * flag; the mean is taken over the per-ray values in a fixed order (bit-reproducible).
  * loss_out: 1 float = kl_div(..., 'mean'). */
+/* lt0 / pin0 may both be NULL: left_tail = Phi((0 - mu) / sigma) and part_inside = Phi((1 - mu) / sigma) - left_tail
+ * (models/models.py:254-258) are then evaluated per coarse cell inside the kernels (constants of the loss, as the
+ * reference detaches them). */
 int ddnerf_dp_loss_forward(const float* t1, const float* t0, const float* w1, const float* w0,
                            const float* mus0, const float* sigmas0, const float* lt0,
                            const float* pin0, int blender, float* loss_out, float* scratch,
