@@ -40,12 +40,16 @@ __global__ void mse_kernel(const float* __restrict__ rgb0, const float* __restri
     }
 }
 
+// torch.optim.Adam rounds its python-double hyper-parameters once: the lerp weight is fl32(1 - beta1) and the addcmul value
+// fl32(1 - beta2) (NOT 1 - fl32(beta): 1 - fl32(0.999) is off by 1.3e-5 relative, which shows in exp_avg_sq), so the
+// complements arrive as their own arguments (omb1, omb2), computed in double on the host.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+                            int64_t n, float lr, float omb1, float b2, float omb2, float eps, float bc1, float bc2_sqrt,
+                            float gscale) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         float gr = __ldg(g + e) * gscale;
-        float mm = m[e] + (gr - m[e]) * (1.0f - b1);           // exp_avg.lerp_(grad, 1-beta1)
-        float vv = v[e] * b2 + (1.0f - b2) * gr * gr;          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+        float mm = m[e] + (gr - m[e]) * omb1;                  // exp_avg.lerp_(grad, 1-beta1)
+        float vv = v[e] * b2 + omb2 * gr * gr;                 // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
         m[e] = mm; v[e] = vv;
         float denom = sqrtf(vv) / bc2_sqrt + eps;
         p[e] -= (lr / bc1) * (mm / denom);
@@ -56,12 +60,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // the learning rate and the bias corrections change from step to step
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 int64_t n, const float* __restrict__ hyper) {
-    const float lr = __ldg(hyper), b1 = __ldg(hyper + 1), b2 = __ldg(hyper + 2), eps = __ldg(hyper + 3);
+    const float lr = __ldg(hyper), b2 = __ldg(hyper + 2), eps = __ldg(hyper + 3);
     const float bc1 = __ldg(hyper + 4), bc2_sqrt = __ldg(hyper + 5), gscale = __ldg(hyper + 6);
+    const float omb1 = __ldg(hyper + 8), omb2 = __ldg(hyper + 9);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         float gr = __ldg(g + e) * gscale;
-        float mm = m[e] + (gr - m[e]) * (1.0f - b1);
-        float vv = v[e] * b2 + (1.0f - b2) * gr * gr;
+        float mm = m[e] + (gr - m[e]) * omb1;
+        float vv = v[e] * b2 + omb2 * gr * gr;
         m[e] = mm; v[e] = vv;
         float denom = sqrtf(vv) / bc2_sqrt + eps;
         p[e] -= (lr / bc1) * (mm / denom);
@@ -73,7 +78,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 // training step then reads nothing the host mutates between replays (a pinned host buffer rewritten in place races with the
 // copy node of an earlier, still queued replay).  One thread, double arithmetic (what the Python driver does), then the
 // counters advance.  state = {iteration i, Adam step count t}; hyper = {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t),
-// grad_scale, gaussian_smooth_factor}.
+// grad_scale, gaussian_smooth_factor, 1-beta1, 1-beta2}.
 struct SchedArgs {
     double lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult;
     double beta1, beta2, eps, grad_scale;
@@ -98,6 +103,8 @@ __global__ void schedule_kernel(long long* __restrict__ state, float* __restrict
     hyper[5] = (float)sqrt(1.0 - pow(a.beta2, (double)t));
     hyper[6] = (float)a.grad_scale;
     hyper[7] = (float)((double)i < a.finnish_smooth ? a.smooth0 - a.dsmooth * (double)i : a.final_smooth);
+    hyper[8] = (float)(1.0 - a.beta1);
+    hyper[9] = (float)(1.0 - a.beta2);
     state[0] = i + 1;
     state[1] = t;
 }
@@ -133,15 +140,16 @@ extern "C" DDNERF_EXPORT int ddnerf_mse_loss(const float* rgb0, const float* rgb
 }
 
 extern "C" DDNERF_EXPORT int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+                                double beta1, double beta2, double eps, int step, float grad_scale, void* stream) {
     DDNERF_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     DDNERF_CHECK_ARG(step >= 1, "adam_step: step=%d must be >= 1", step);
     if (n == 0) return 0;
-    float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-    float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    float bc1 = (float)(1.0 - pow(beta1, (double)step));
+    float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
     int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                        eps, bc1, bc2_sqrt, grad_scale);
+    adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, (float)(1.0 - beta1),
+                                                                        (float)beta2, (float)(1.0 - beta2), (float)eps, bc1,
+                                                                        bc2_sqrt, grad_scale);
     DDNERF_LAUNCHED("adam_step", 1);
     return 0;
 }

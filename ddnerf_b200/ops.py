@@ -407,11 +407,13 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
 
 
 def adam_step_dev(param, grad, exp_avg, exp_avg_sq, hyper):
-    """adam_step with {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale} read from the device
-    tensor `hyper` (7 floats): graph-replayable."""
+    """adam_step with {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, -, 1-beta1, 1-beta2} read from the
+    device tensor `hyper` (10 floats, what ddnerf_train_schedule writes): graph-replayable."""
     lib = _lib.load()
     for t in (param, grad, exp_avg, exp_avg_sq, hyper):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise RuntimeError("ddnerf_b200: adam_step_dev needs contiguous fp32 CUDA buffers")
+    if hyper.numel() < 10:
+        raise RuntimeError("ddnerf_b200: adam_step_dev needs the 10-float hyper record of ddnerf_train_schedule")
     _lib.check(lib.ddnerf_adam_step_dev(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(hyper), _stream()),
                "adam_step_dev")

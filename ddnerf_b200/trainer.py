@@ -199,8 +199,8 @@ class Trainer:
         self._static = None
         dev = self.buckets[0].flat.device
         if self.use_graph:
-            # [lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, gaussian_smooth_factor]
-            self._hyper_dev = torch.zeros(8, device=dev, dtype=torch.float32)
+            # [lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, gaussian_smooth_factor, 1 - beta1, 1 - beta2]
+            self._hyper_dev = torch.zeros(10, device=dev, dtype=torch.float32)
             self._sched_state = torch.zeros(2, device=dev, dtype=torch.int64)      # {iteration, Adam steps taken}
 
     # ---- checkpoints in the reference's format (train_model.py:248-263 save, :77-81,110-118 resume) ---------------
@@ -309,8 +309,8 @@ class Trainer:
         import ctypes
         from . import _lib
         tp = self.cfg.train_params
-        f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))      # the eager kernels take these as fp32 arguments
-        sched = (ctypes.c_double * 13)(0.0005, 5e-6, float(self.train_iters), 2500.0, 0.01, f32(0.9), f32(0.999), f32(1e-8),
+        f32 = lambda x: float(torch.tensor(x, dtype=torch.float32))      # the eager kernel takes grad_scale as fp32
+        sched = (ctypes.c_double * 13)(0.0005, 5e-6, float(self.train_iters), 2500.0, 0.01, 0.9, 0.999, 1e-8,
                                        f32(1.0 / self.world), float(self._smooth0), float(self._dsmooth),
                                        float(tp.final_smooth), float(tp.finnish_smooth))
         _lib.check(_lib.load().ddnerf_train_schedule(ctypes.c_void_p(self._sched_state.data_ptr()),

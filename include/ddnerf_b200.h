@@ -279,11 +279,12 @@ int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, f
 /* torch.optim.Adam (no weight decay, no amsgrad) on a flat fp32 bucket; grad_scale multiplies
  * the gradient first (1/world_size after an all-reduce sum). */
 int ddnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                     int64_t n, float lr, float beta1, float beta2, float eps, int step,
+                     int64_t n, float lr, double beta1, double beta2, double eps, int step,
                      float grad_scale, void* stream);
 
-/* The same update with its scalars in device memory: hyper[7] = {lr, beta1, beta2, eps, 1 - beta1^step,
- * sqrt(1 - beta2^step), grad_scale}.  Lets a CUDA graph of the whole training step be replayed while the
+/* The same update with its scalars in device memory: hyper[10] = {lr, beta1, beta2, eps, 1 - beta1^step,
+ * sqrt(1 - beta2^step), grad_scale, (unused here), 1 - beta1, 1 - beta2} (the complements rounded from double, as
+ * torch.optim.Adam passes them).  Lets a CUDA graph of the whole training step be replayed while the
  * learning rate and bias corrections change every step. */
 int ddnerf_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                          int64_t n, const float* hyper, void* stream);
@@ -292,7 +293,8 @@ int ddnerf_adam_step_dev(float* param, const float* grad, float* exp_avg, float*
  * learning_rate_decay of general_utils/nerf_helpers.py:211-245) and Adam's bias corrections, computed on the device
  * from a device-resident counter so that a replayed CUDA graph of the step reads nothing the host mutates.
  * state[2] (int64, device) = {iteration i, Adam steps taken}: read, then both advanced by one.
- * hyper[8] (device) receives {lr(i), beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, smooth(i)}, t = steps + 1.
+ * hyper[10] (device) receives {lr(i), beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, smooth(i), 1-beta1,
+ * 1-beta2}, t = steps + 1.
  * sched[13] (HOST doubles, read at call time) = {lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult, beta1,
  * beta2, eps, grad_scale, smooth0, dsmooth, final_smooth, finnish_smooth}. */
 int ddnerf_train_schedule(int64_t* state, float* hyper, const double* sched, void* stream);
