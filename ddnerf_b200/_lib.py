@@ -51,6 +51,8 @@ SIGNATURES = {
     "ddnerf_mlp_tc_pack": (c_i, [ctypes.POINTER(MlpPtrs), c_i, c_p, c_p, c_p]),
     "ddnerf_mlp_tc_encode": (c_i, [c_p, c_p, c_l, c_i, c_i, c_p, c_p]),
     "ddnerf_mlp_tc_forward": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
+    "ddnerf_mlp_tc_enc_scratch_bytes": (c_l, []),
+    "ddnerf_mlp_tc_forward_rays": (c_i, [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ddnerf_mlp_tc_backward_dx": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_p]),
     "ddnerf_mlp_tc_backward_dw": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(MlpPtrs), c_l, c_i, c_i, c_p]),
     "ddnerf_mlp_tc_program_check": (c_i, []),

@@ -11,7 +11,11 @@
 //                    tile's MMAs;
 //   8 epilogue warps: tcgen05.ld the accumulator, add bias, ReLU, convert to bf16 and write the next
 //                    layer's A operand in place (K-major SWIZZLE_128B); density / colour / (mu, sigma)
-//                    heads are extra columns of the last two GEMMs and leave as fp32.
+//                    heads are extra columns of the last two GEMMs and leave as fp32;
+//   2 encoder warps : (forward) cone -> Gaussian, integrated positional encoding and view-direction encoding
+//                    (models.py:117-133) of the work item AFTER the one in flight, written as the bf16 operand image
+//                    the producer streams into the ring -- a per-CTA double buffer that never leaves L2 at inference,
+//                    the saved image the weight-gradient kernel reads in training.  No separate encode launch.
 //
 // FORWARD (program 0): layers_xyz.0-7, fc_feat, [layers_dir.0 | fc_alpha], [fc_rgb | fc_mu_sigma].
 // The skip connection cat(xyz, h) of layer 5 and the cat(feat, dirs) of the view branch are extra
@@ -44,7 +48,12 @@ __constant__ PackTable c_pack;
 struct ChainArgs {
     const uint8_t* wimg;      // packed weight stages of this program (program order)
     const float* bias;        // fwd: packed fp32 biases, [n_epis][256]
-    const uint8_t* enc;       // fwd: encoded-feature images, [n_items][64 KB]
+    const uint8_t* enc;       // fwd: encoded-feature images: enc_mode 0/1 [n_items][64 KB], enc_mode 2 [grid][2][64 KB]
+    // in-kernel encoder (enc_mode 1: writes the full image, training; 2: per-CTA double buffer, inference; 0: image given)
+    const float* rays;        // [N,12]
+    const float* t_vals;      // [N,S+1]
+    int64_t N;
+    int S, ray_shape, enc_mode;
     float* out;               // fwd: [rows, C]
     const float* gout;        // bwd: [rows, C] cotangent of the output
     uint8_t* save;            // fwd: act_save or null; bwd: dz_save.  [layers][n_tiles][64 KB]
@@ -63,6 +72,7 @@ constexpr uint32_t kHi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) 
 
 struct __align__(16) SmemCtl {
     uint64_t full[kSlots], empty[kSlots], acc_full[2], act_ready[2];
+    uint64_t enc_ready[2], enc_free[2];  // encoder -> producer: image of item parity p written; MMA warp -> encoder: consumed
     uint32_t tmem_base, pad[3];
     float bias[2][256];
 };
@@ -394,9 +404,10 @@ __device__ void producer_role(const ChainArgs& g, SmemCtl* ctl, uint8_t* ring) {
     const int n_loads = P.n_loads;                         // multiple of kSlots
     // every CTA re-reads the 2.4 MB of packed weights for each work item: keep them in L2 against the streaming saves
     const uint64_t pol_w = tc::l2_policy_evict_last(), pol_in = tc::l2_policy_evict_first();
-    uint32_t phase = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-        const uint8_t* enc = g.enc + (size_t)item * kEncItemBytes;
+    uint32_t phase = 0, n = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
+        const uint8_t* enc = g.enc + (g.enc_mode == 2 ? (size_t)(blockIdx.x * 2u + (n & 1u)) : (size_t)item) * kEncItemBytes;
+        if (PI == 0 && g.enc_mode) tc::mbar_wait(&ctl->enc_ready[n & 1u], (n >> 1) & 1u);      // the encoder warps wrote it
         int slot = 0;
         for (int i = 0; i < n_loads; ++i) {
             const Load L = P.loads[i];
@@ -492,7 +503,8 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
     const unsigned long long t_begin = clk();
     const int n_mmas = P.n_mmas;
     bool first_item = true;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+    uint32_t n_item = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n_item) {
         for (int i = 0; i < n_mmas; ++i) {
             const uint4 q0 = *reinterpret_cast<const uint4*>(&P.mmas[i]);
             const uint4 q1 = *(reinterpret_cast<const uint4*>(&P.mmas[i]) + 1);
@@ -504,6 +516,7 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
             const uint32_t tile = q1.z & 0xFFu, n_wait = (q1.z >> 8) & 0xFFu, rel0 = (q1.z >> 16) & 0xFFu, rel1 = q1.z >> 24;
             if ((flags & F_WAIT_ACT) || ((flags & F_WAIT_PREV) && !first_item)) S.wait_act(tile);
             for (uint32_t w = 0; w < n_wait; ++w) S.wait_stage();
+            if (PI == 0 && (flags & F_ENC_DONE) && tc::elect_one()) tc::mbar_arrive(&ctl->enc_free[n_item & 1u]);
             tc::tc_fence_after_sync();
             if (tc::elect_one()) {
                 const uint64_t a = ((uint64_t)q0.z << 32) | (uint64_t)(S.base16 + q0.x);
@@ -527,6 +540,8 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
     }
 }
 
+__device__ void encoder_role(const ChainArgs& g, SmemCtl* ctl, int tid);
+
 template <int PI>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -541,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainAr
     if (warp == 9 && lane == 0) {
         for (int s = 0; s < kSlots; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
         for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 1); }
+        for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->enc_ready[t], 1); tc::mbar_init(&ctl->enc_free[t], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 8) tc::tmem_alloc(&ctl->tmem_base, 512);
@@ -553,8 +569,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainAr
         else epilogue_bwd(g, ctl, act_all, warp, lane);
     } else if (warp == 8) {
         if (lane == 0) producer_role<PI>(g, ctl, ring);
-    } else {
+    } else if (warp == 9) {
         mma_role<PI>(g, ctl, tc::smem_u32(smem));
+    } else {
+        if (PI == 0 && g.enc_mode) encoder_role(g, ctl, (int)threadIdx.x - 320);
     }
 
     tc::tc_fence_before_sync();
@@ -638,14 +656,9 @@ __device__ __forceinline__ float safe_arg_fast(float x) {          // math_utils
     return fmaf(-q, T, x);
 }
 
-__global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
-                                                         uint8_t* __restrict__ img, int64_t N, int S, int ray_shape,
-                                                         int64_t rows_padded) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows_padded) return;
-    const int64_t item = row / kItemRows;
-    const int T = (int)(row % kItemRows) / 128, r = (int)(row % 128);
-    uint8_t* ib = img + item * kEncItemBytes;
+// one sample row of the operand image: `row` = global sample row, (T, r) = its tile and row inside the 256-row item at `ib`
+__device__ __forceinline__ void encode_row_image(const float* __restrict__ rays, const float* __restrict__ t_vals, int64_t N, int S,
+                                                 int ray_shape, int64_t row, uint8_t* __restrict__ ib, int T, int r) {
     uint32_t w[48];                       // 96 bf16: feature f = h*48 + l*3 + a in word f/2
     uint32_t dw[16];                      // 32 bf16 of the direction block
 #pragma unroll
@@ -703,6 +716,35 @@ __global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(dp + (((uint32_t)j ^ sw) << 4)) = make_uint4(dw[4 * j], dw[4 * j + 1], dw[4 * j + 2], dw[4 * j + 3]);
+}
+
+__global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict__ rays, const float* __restrict__ t_vals,
+                                                         uint8_t* __restrict__ img, int64_t N, int S, int ray_shape,
+                                                         int64_t rows_padded) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_padded) return;
+    const int64_t item = row / kItemRows;
+    encode_row_image(rays, t_vals, N, S, ray_shape, row, img + item * kEncItemBytes, (int)(row % kItemRows) / 128, (int)(row % 128));
+}
+
+// The encoder warps of the forward chain kernel (2 warps, 4 sample rows per thread and item).  They run one to two work
+// items ahead of the GEMMs: item n of this CTA goes to image slot (n & 1) as soon as the MMA warp has seen the last encoded
+// block of item n - 2 land in the ring, the producer starts item n's loads when the image is complete.  The image is
+// written with ordinary stores and read back by the TMA engine (bulk copies): fence.proxy.async orders the two proxies,
+// the named barrier + mbarrier arrive / wait carry the release / acquire.
+__device__ void encoder_role(const ChainArgs& g, SmemCtl* ctl, int tid) {
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
+        const uint32_t par = n & 1u;
+        if (n >= 2) tc::mbar_wait(&ctl->enc_free[par], ((n >> 1) - 1u) & 1u);
+        uint8_t* ib = const_cast<uint8_t*>(g.enc) + (g.enc_mode == 2 ? (size_t)(blockIdx.x * 2u + par) : (size_t)item) * kEncItemBytes;
+#pragma unroll 1
+        for (int rr = tid; rr < kItemRows; rr += kEncThreads)
+            encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, (int64_t)item * kItemRows + rr, ib, rr >> 7, rr & 127);
+        tc::fence_proxy_async_all();
+        named_bar(2, kEncThreads);
+        if (tid == 0) tc::mbar_arrive(&ctl->enc_ready[par]);
+    }
 }
 
 // ---- host: program construction ----------------------------------------------------------------
@@ -869,7 +911,7 @@ void build_fwd(Builder& b) {
             for (int T = 0; T < 2; ++T) {
                 for (int c = 4 * h; c < 4 * h + 4; ++c)
                     b.mma(T, c == 0 ? (F_FIRST | F_WAIT_ACT) : 0, 2, 144, -1, (c / 2) * 16384u + (c % 2) * 64u, w[c], 0, T == 1 ? w[c] : -1);
-                if (h == 1) b.mma(T, F_COMMIT_ACC, 2, 144, d, T * 8192u, w[8], 0, T == 1 ? w[8] : -1, T == 1 ? d : -1);
+                if (h == 1) b.mma(T, F_COMMIT_ACC | (T == 0 ? F_ENC_DONE : 0), 2, 144, d, T * 8192u, w[8], 0, T == 1 ? w[8] : -1, T == 1 ? d : -1);
             }
         b.epi(EPI_DIR, 1, 9, -1, 144, 9, 32768);
     }
@@ -1017,6 +1059,19 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_encode(const float* rays, const float
     return 0;
 }
 
+static int launch_forward(const char* who, ChainArgs g, int64_t rows, void* stream) {
+    const int64_t n_items = ddnerf_mlp_tc_items(rows);
+    DDNERF_CHECK_ARG(n_items < (1 << 30), "%s: too many rows", who);
+    g.rows = rows;
+    g.n_items = (int)n_items;
+    if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
+    g.prof = g_prof_buffer;
+    const int grid = (int)std::min<int64_t>(n_items, sm_count());
+    mlp_tc_chain_kernel<0><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    DDNERF_LAUNCHED(who, 1);
+    return 0;
+}
+
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float* bias_pack, const void* enc_img, int64_t rows,
                                                    int out_channels, float* out, void* act_save, void* mask_save, void* stream) {
     DDNERF_CHECK_ARG(wimg && bias_pack && enc_img && out, "mlp_tc_forward: null pointer");
@@ -1025,24 +1080,50 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward(const void* wimg, const float
     DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_forward: the bf16 MLP needs an sm_100 device (tcgen05)");
     if (rows == 0) return 0;
     TC_ENSURE("mlp_tc_forward");
-    const int64_t n_items = ddnerf_mlp_tc_items(rows);
-    DDNERF_CHECK_ARG(n_items < (1 << 30), "mlp_tc_forward: too many rows");
     ChainArgs g{};
     g.wimg = static_cast<const uint8_t*>(wimg);
     g.bias = bias_pack;
     g.enc = static_cast<const uint8_t*>(enc_img);
+    g.enc_mode = 0;
     g.out = out;
     g.save = static_cast<uint8_t*>(act_save);
     g.mask = static_cast<uint32_t*>(mask_save);
-    g.rows = rows;
-    g.n_items = (int)n_items;
     g.C = out_channels;
-    if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
-    g.prof = g_prof_buffer;
-    const int grid = (int)std::min<int64_t>(n_items, sm_count());
-    mlp_tc_chain_kernel<0><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
-    DDNERF_LAUNCHED("mlp_tc_forward", 1);
-    return 0;
+    return launch_forward("mlp_tc_forward", g, rows, stream);
+}
+
+extern "C" DDNERF_EXPORT int64_t ddnerf_mlp_tc_enc_scratch_bytes(void) { return (int64_t)sm_count() * 2 * tcmlp::kEncItemBytes; }
+
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_forward_rays(const void* wimg, const float* bias_pack, const float* rays,
+                                                        const float* t_vals, int64_t N, int S, int ray_shape, int out_channels,
+                                                        float* out, void* enc_img, void* enc_scratch, void* act_save,
+                                                        void* mask_save, void* stream) {
+    DDNERF_CHECK_ARG(wimg && bias_pack && rays && t_vals && out, "mlp_tc_forward_rays: null pointer");
+    DDNERF_CHECK_ARG((enc_img != nullptr) != (enc_scratch != nullptr),
+                     "mlp_tc_forward_rays: give either enc_img (kept for the backward) or enc_scratch (inference)");
+    DDNERF_CHECK_ARG(out_channels == 4 || out_channels == 6, "mlp_tc_forward_rays: out_channels=%d (4 or 6)", out_channels);
+    DDNERF_CHECK_ARG((act_save == nullptr) == (mask_save == nullptr), "mlp_tc_forward_rays: act_save and mask_save go together");
+    DDNERF_CHECK_ARG(!act_save || enc_img, "mlp_tc_forward_rays: the training forward needs enc_img (the weight-gradient kernel reads it)");
+    DDNERF_CHECK_ARG(ray_shape == 0 || ray_shape == 1, "mlp_tc_forward_rays: ray_shape=%d (0 cone, 1 cylinder)", ray_shape);
+    DDNERF_CHECK_ARG(S >= 1 && N >= 0, "mlp_tc_forward_rays: N=%lld S=%d", (long long)N, S);
+    DDNERF_CHECK_ARG(ddnerf_device_is_sm100(), "mlp_tc_forward_rays: the bf16 MLP needs an sm_100 device (tcgen05)");
+    if (N == 0) return 0;
+    TC_ENSURE("mlp_tc_forward_rays");
+    ChainArgs g{};
+    g.wimg = static_cast<const uint8_t*>(wimg);
+    g.bias = bias_pack;
+    g.enc = static_cast<const uint8_t*>(enc_img ? enc_img : enc_scratch);
+    g.enc_mode = enc_img ? 1 : 2;
+    g.rays = rays;
+    g.t_vals = t_vals;
+    g.N = N;
+    g.S = S;
+    g.ray_shape = ray_shape;
+    g.out = out;
+    g.save = static_cast<uint8_t*>(act_save);
+    g.mask = static_cast<uint32_t*>(mask_save);
+    g.C = out_channels;
+    return launch_forward("mlp_tc_forward_rays", g, N * (int64_t)S, stream);
 }
 
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const float* bias_pack, const float* grad_out,

@@ -22,13 +22,15 @@ constexpr int kSlotBytes = 16384;
 constexpr int kActBytes = 65536;
 constexpr int kItemRows = 256;
 constexpr int kEncItemBytes = 65536;     // [T0 b0,b1 | T1 b0,b1 | T0 b2 | T1 b2 | T0 dir | T1 dir], blocks [128 x 32] SW64
-constexpr int kThreads = 320;            // warps 0-7 epilogue (4 per tile), 8 producer, 9 MMA issuer
+constexpr int kThreads = 384;            // warps 0-7 epilogue (4 per tile), 8 producer, 9 MMA issuer, 10-11 encoder (forward)
+constexpr int kEncThreads = 64;
 constexpr int kMaxLoads = 96, kMaxMmas = 208, kMaxEpis = 12, kMaxPack = 192;
 constexpr int kSaveLayers = 10;
 constexpr int kBiasRows = 16, kHeadWRow = 11;     // packed fp32 table: 11 bias rows + 5 head-weight rows
 constexpr uint32_t kRingOff = 2 * kActBytes;          // smem byte offset of the ring
 
-enum : uint8_t { F_WAIT_ACT = 1, F_FIRST = 2, F_COMMIT_ACC = 4, F_WAIT_PREV = 16 };
+enum : uint8_t { F_WAIT_ACT = 1, F_FIRST = 2, F_COMMIT_ACC = 4, F_WAIT_PREV = 16,
+                 F_ENC_DONE = 32 };       // the item's last encoded block has landed in the ring: its image may be overwritten
 enum : uint8_t { EPI_ACT = 0, EPI_DIR = 1, EPI_OUT = 2, EPI_BWD_IN = 3, EPI_BWD_MASK = 4 };
 enum : uint8_t { LOAD_W = 0, LOAD_ENC = 1 };
 

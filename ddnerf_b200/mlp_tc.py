@@ -48,7 +48,9 @@ def _state(module):
 
 
 def encode_img(rays, t_vals, ray_shape="cone"):
-    """rays [N,12], t_vals [N,S+1] -> bf16 operand images of all 256-row work items (uint8 tensor)."""
+    """rays [N,12], t_vals [N,S+1] -> bf16 operand images of all 256-row work items (uint8 tensor), by the STANDALONE
+    encoder kernel.  The model path no longer calls it (the chain kernel encodes in its own warps); kept for the layout
+    tests and for callers of the image-fed entry point ddnerf_mlp_tc_forward."""
     lib = _lib.load()
     rays, t_vals = _req(rays, "rays"), _req(t_vals.detach(), "t_vals")
     N, S = rays.shape[0], t_vals.shape[1] - 1
@@ -57,18 +59,37 @@ def encode_img(rays, t_vals, ray_shape="cone"):
     return img
 
 
+_ENC_SCRATCH = {}
+
+
+def _enc_scratch(dev):
+    """Per-device double buffer of the in-kernel encoder (2 x 64 KB per SM; lives in L2).  Launches on one stream are
+    ordered, so one buffer per (device, stream) serves every inference call."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ENC_SCRATCH.get(key)
+    if buf is None:
+        buf = torch.empty(_lib.load().ddnerf_mlp_tc_enc_scratch_bytes(), device=dev, dtype=torch.uint8)
+        _ENC_SCRATCH[key] = buf
+    return buf
+
+
 def forward_only(module, rays, t_vals, ray_shape="cone"):
-    """Inference forward: [N*S, C] fp32 raw network outputs."""
+    """Inference forward: [N*S, C] fp32 raw network outputs.  ONE launch: the chain kernel's encoder warps compute the
+    integrated positional encoding of work item n+1 while the GEMMs of item n run (no encoded image in HBM)."""
     lib = _lib.load()
     st = _state(module)
     st.refresh()
+    rays, t_vals = _req(rays, "rays"), _req(t_vals.detach(), "t_vals")
     N, S = rays.shape[0], t_vals.shape[1] - 1
     rows = N * S
-    img = encode_img(rays, t_vals, ray_shape)
     out = torch.empty(rows, module.out_channels, device=rays.device, dtype=torch.float32)
+    if rows == 0:
+        return out
+    scratch = _enc_scratch(rays.device)
     with _mlp_timer():
-        _lib.check(lib.ddnerf_mlp_tc_forward(_p(st.wimg), _p(st.bias), _p(img), rows, module.out_channels, _p(out), None, None,
-                                             _stream()), "mlp_tc_forward")
+        _lib.check(lib.ddnerf_mlp_tc_forward_rays(_p(st.wimg), _p(st.bias), _p(rays), _p(t_vals), N, S, RAY_SHAPES[ray_shape],
+                                                  module.out_channels, _p(out), None, _p(scratch), None, None, _stream()),
+                   "mlp_tc_forward_rays")
     return out
 
 
@@ -84,13 +105,15 @@ class _MlpTc(torch.autograd.Function):
         st.refresh()
         N, S = rays.shape[0], t_vals.shape[1] - 1
         rows, C, dev = N * S, module.out_channels, rays.device
-        img = encode_img(rays, t_vals, ray_shape)
+        # the operand image is written by the forward kernel's encoder warps and kept for the weight-gradient kernel
+        img = torch.empty(max(lib.ddnerf_mlp_tc_enc_bytes(rows), 16), device=dev, dtype=torch.uint8)
         out = torch.empty(rows, C, device=dev, dtype=torch.float32)
         act = torch.empty(max(lib.ddnerf_mlp_tc_act_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
         mask = torch.empty(max(lib.ddnerf_mlp_tc_mask_save_bytes(rows), 16), device=dev, dtype=torch.uint8)
         with _mlp_timer("fwd"):
-            _lib.check(lib.ddnerf_mlp_tc_forward(_p(st.wimg), _p(st.bias), _p(img), rows, C, _p(out), _p(act), _p(mask),
-                                                 _stream()), "mlp_tc_forward")
+            _lib.check(lib.ddnerf_mlp_tc_forward_rays(_p(st.wimg), _p(st.bias), _p(rays), _p(t_vals), N, S,
+                                                      RAY_SHAPES[ray_shape], C, _p(out), _p(img), None, _p(act), _p(mask),
+                                                      _stream()), "mlp_tc_forward_rays")
         ctx.st, ctx.img, ctx.act, ctx.mask = st, img, act, mask
         ctx.rows, ctx.C = rows, C
         ctx.sink = getattr(module, "_grad_sink", None)

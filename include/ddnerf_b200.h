@@ -147,6 +147,16 @@ int ddnerf_mlp_tc_backward_dw(const void* act_save, const void* dz_save, const v
  * (0 = consistent) and the split of backward_dw over `sms` SMs: the (layer-op, tile) line cut into at most `sms`
  * equal-cost pieces, a piece that crosses a layer-op boundary being two (rarely three) work items run back to back by
  * one CTA; written as (op, first tile, end tile) uint32 triples; returns the number of work items (<= sms + 12). */
+/* The forward with the encoder inside the kernel (models/models.py:117-142 as ONE launch): two extra warps of the chain
+ * kernel compute cone -> Gaussian, IPE and the view-direction encoding of the next 256-row work item while the GEMMs of
+ * the current one run.  Give enc_img (ddnerf_mlp_tc_enc_bytes(N*S) bytes, written here and read by
+ * ddnerf_mlp_tc_backward_dw) for the training forward, or enc_scratch (ddnerf_mlp_tc_enc_scratch_bytes() bytes, a
+ * per-SM double buffer that stays in L2) for inference -- exactly one of the two. */
+int64_t ddnerf_mlp_tc_enc_scratch_bytes(void);
+int ddnerf_mlp_tc_forward_rays(const void* wimg, const float* bias_pack, const float* rays,
+                               const float* t_vals, int64_t N, int S, int ray_shape, int out_channels,
+                               float* out, void* enc_img, void* enc_scratch, void* act_save,
+                               void* mask_save, void* stream);
 int ddnerf_mlp_tc_program_check(void);
 /* Diagnostic hook of the dW kernel: a device buffer of >= 4 * 480 uint64 receives, per work item of the next
  * launches, {layer-op, tiles, cycles until its last MMA completed, cycles of its flush}; NULL switches it off. */

@@ -477,10 +477,40 @@ def _decode_enc_image(img, rows):
     return to_f(ipe)[:rows], to_f(dirs)[:rows]
 
 
-@pytest.mark.parametrize("kind,N,S", [("blender", 37, 16), ("ff", 64, 32), ("360", 9, 128)])
-def test_encode_img_vs_oracle(kind, N, S):
+def _chain_encoder_image(rays, t_vals):
+    """The operand image written by the ENCODER WARPS of the forward chain kernel (training forward: the image is kept for
+    the weight-gradient kernel), through the C ABI."""
+    import ctypes
+    from ddnerf_b200 import _lib, mlp_tc
+    from ddnerf_b200.models import base_architectures as BA
+    from oracle import ddnerf_oracle as orc
+    lib = _lib.load()
+    net = BA.MipNeRFModel(hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True)
+    net.load_state_dict(orc.init_mlp_params(False, seed=1))
+    net.to("cuda")
+    st = mlp_tc._state(net)
+    st.refresh()
+    N, S = rays.shape[0], t_vals.shape[1] - 1
+    rows = N * S
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    img = torch.full((lib.ddnerf_mlp_tc_enc_bytes(rows),), 0xAB, device="cuda", dtype=torch.uint8)
+    out = torch.empty(rows, 4, device="cuda")
+    act = torch.empty(lib.ddnerf_mlp_tc_act_save_bytes(rows), device="cuda", dtype=torch.uint8)
+    mask = torch.empty(lib.ddnerf_mlp_tc_mask_save_bytes(rows), device="cuda", dtype=torch.uint8)
+    _lib.check(lib.ddnerf_mlp_tc_forward_rays(P(st.wimg), P(st.bias), P(rays), P(t_vals), N, S, 0, 4, P(out), P(img), None, P(act),
+                                              P(mask), None), "mlp_tc_forward_rays")
+    torch.cuda.synchronize()
+    return img
+
+
+@pytest.mark.parametrize("source", ["chain_kernel_encoder_warps", "standalone_kernel"])
+@pytest.mark.parametrize("kind,N,S", [("blender", 37, 16), ("ff", 64, 32), ("360", 9, 128), ("blender", 700, 64)])
+def test_encode_img_vs_oracle(kind, N, S, source):
     """K2 in bf16 mode: every feature of the operand image within one bf16 step of the oracle's fp32 encoding
-    (integrated positional encoding, math_utils.py:112-166, and the view-direction encoding, nerf_helpers.py:127-171)."""
+    (integrated positional encoding, math_utils.py:112-166, and the view-direction encoding, nerf_helpers.py:127-171) --
+    for the image the forward chain kernel's own encoder warps write (the model path; 700 x 64 rows = 175 work items, more
+    than one per CTA, so the double-buffer hand-shake between encoder, producer and MMA warps is exercised) and for the
+    standalone encoder kernel."""
     from oracle import ddnerf_oracle as orc
     from ddnerf_b200 import mlp_tc
     from ddnerf_b200.rays import synth_rays
@@ -489,7 +519,10 @@ def test_encode_img_vs_oracle(kind, N, S):
     g = torch.Generator().manual_seed(5)
     t = orc.sample_first_cycle(torch.full((N, 1), near), torch.full((N, 1), far), S, False, torch.rand(N, S + 1, generator=g))
     ref = orc.encode_rows(rays, t)                                       # [N*S, 123] fp32
-    img = mlp_tc.encode_img(rays.cuda(), t.cuda())
+    if source == "standalone_kernel":
+        img = mlp_tc.encode_img(rays.cuda(), t.cuda())
+    else:
+        img = _chain_encoder_image(rays.cuda().contiguous(), t.cuda().contiguous())
     ipe, dirs = _decode_enc_image(img, N * S)
     for got, want in ((ipe, ref[:, :96]), (dirs[:, :27], ref[:, 96:])):
         err = (got - want).abs()

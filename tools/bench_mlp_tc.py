@@ -72,6 +72,25 @@ def main():
     ms = e0.elapsed_time(e1) / args.iters
     flops = 2.0 * 610304 * rows
     res.update(rows=rows, fwd_ms=ms, fwd_tflops=flops / ms / 1e9, save=bool(args.save))
+
+    # the model path: ONE launch, the chain kernel's own encoder warps (no standalone encode)
+    scratch = torch.empty(lib.ddnerf_mlp_tc_enc_scratch_bytes(), device="cuda", dtype=torch.uint8)
+    img2 = torch.empty_like(img) if args.save else None
+
+    def fwd_rays():
+        _lib.check(lib.ddnerf_mlp_tc_forward_rays(_p(st.wimg), _p(st.bias), _p(rays), _p(t_vals), N, S, 0, 4, _p(out), _p(img2),
+                                                  None if args.save else _p(scratch), _p(act), _p(mask), _stream()), "fwd_rays")
+
+    for _ in range(3):
+        fwd_rays()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.iters):
+        fwd_rays()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    res.update(fwd_rays_ms=ms, fwd_rays_tflops=flops / ms / 1e9, encode_plus_fwd_ms=res["encode_ms"] + res["fwd_ms"])
     if args.save:
         dz = torch.empty_like(act)
         gout = torch.randn(rows, 4, device="cuda")
