@@ -25,29 +25,38 @@ __device__ __forceinline__ RayGeom load_ray(const float* __restrict__ rays, int6
 
 struct Gauss3 { float mx, my, mz, cx, cy, cz; };
 
-// interval (t0,t1) of a ray -> diagonal Gaussian (mean, cov_diag)
+// interval (t0,t1) of a ray -> diagonal Gaussian (mean, cov_diag).
+// Written with the round-to-nearest intrinsics, which the compiler never contracts into FMAs: the encoding at level l
+// multiplies the mean by 2^l, so ONE ulp of the mean is 2^l ulps of phase (5e-4 rad at l = 10) -- the reference's own
+// features are that sensitive to its op-by-op fp32 rounding, and every compile unit (the fp32 encoder built with
+// -fmad=false, the bf16 MLP kernels built with contraction on) must reproduce it bit for bit.
 __device__ __forceinline__ Gauss3 cast_interval(const RayGeom& g, float t0, float t1, int ray_shape) {
+    const auto mul = [](float a, float b) { return __fmul_rn(a, b); };
+    const auto add = [](float a, float b) { return __fadd_rn(a, b); };
+    const auto sub = [](float a, float b) { return __fsub_rn(a, b); };
+    const auto div = [](float a, float b) { return __fdiv_rn(a, b); };
     float t_mean, t_var, r_var;
+    const float rad2 = mul(g.rad, g.rad);
     if (ray_shape == 0) {                                   // cone, math_utils.py:76-82
-        float mu = (t0 + t1) / 2.0f, hw = (t1 - t0) / 2.0f;
-        float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2;
-        float den = 3.0f * mu2 + hw2;
-        t_mean = mu + (2.0f * mu * hw2) / den;
-        t_var = hw2 / 3.0f - (float)(4.0 / 15.0) * ((hw4 * (12.0f * mu2 - hw2)) / (den * den));
-        r_var = (g.rad * g.rad) * (mu2 / 4.0f + (float)(5.0 / 12.0) * hw2 - (float)(4.0 / 15.0) * hw4 / den);
+        const float mu = div(add(t0, t1), 2.0f), hw = div(sub(t1, t0), 2.0f);
+        const float mu2 = mul(mu, mu), hw2 = mul(hw, hw), hw4 = mul(hw2, hw2);
+        const float den = add(mul(3.0f, mu2), hw2);
+        t_mean = add(mu, div(mul(mul(2.0f, mu), hw2), den));
+        t_var = sub(div(hw2, 3.0f), mul((float)(4.0 / 15.0), div(mul(hw4, sub(mul(12.0f, mu2), hw2)), mul(den, den))));
+        r_var = mul(rad2, sub(add(div(mu2, 4.0f), mul((float)(5.0 / 12.0), hw2)), div(mul((float)(4.0 / 15.0), hw4), den)));
     } else {                                                // cylinder, math_utils.py:107-109
-        t_mean = (t0 + t1) / 2.0f;
-        r_var = (g.rad * g.rad) / 4.0f;
-        float d = t1 - t0;
-        t_var = (d * d) / 12.0f;
+        t_mean = div(add(t0, t1), 2.0f);
+        r_var = div(rad2, 4.0f);
+        const float d = sub(t1, t0);
+        t_var = div(mul(d, d), 12.0f);
     }
-    float dx2 = g.dx * g.dx, dy2 = g.dy * g.dy, dz2 = g.dz * g.dz;
-    float dmag = fmaxf(1e-10f, dx2 + dy2 + dz2);            // math_utils.py:38
+    const float dx2 = mul(g.dx, g.dx), dy2 = mul(g.dy, g.dy), dz2 = mul(g.dz, g.dz);
+    const float dmag = fmaxf(1e-10f, add(add(dx2, dy2), dz2));            // math_utils.py:38
     Gauss3 o;
-    o.mx = g.dx * t_mean + g.ox; o.my = g.dy * t_mean + g.oy; o.mz = g.dz * t_mean + g.oz;
-    o.cx = t_var * dx2 + r_var * (1.0f - dx2 / dmag);
-    o.cy = t_var * dy2 + r_var * (1.0f - dy2 / dmag);
-    o.cz = t_var * dz2 + r_var * (1.0f - dz2 / dmag);
+    o.mx = add(mul(g.dx, t_mean), g.ox); o.my = add(mul(g.dy, t_mean), g.oy); o.mz = add(mul(g.dz, t_mean), g.oz);
+    o.cx = add(mul(t_var, dx2), mul(r_var, sub(1.0f, div(dx2, dmag))));
+    o.cy = add(mul(t_var, dy2), mul(r_var, sub(1.0f, div(dy2, dmag))));
+    o.cz = add(mul(t_var, dz2), mul(r_var, sub(1.0f, div(dz2, dmag))));
     return o;
 }
 
