@@ -339,6 +339,57 @@ def run_render(args, dev, world, rank, dist):
             "frames": frames, "chunk_rays": int(cfg.nerf.validation.chunksize)}
 
 
+def run_train_block(args, wl_name, dev, world, rank, dist, K, W):
+    """A second training workload in the same line (weak scaling, rays per GPU fixed): BASELINE.json configs[3] --
+    config_360.yml DDNeRF, 16,384 rays per GPU, 32 + 32 samples, gradient all-reduce of both networks' flat buckets --
+    so that the scaling run covers the configuration BASELINE.json names for multi-GPU training.  Inputs resident in HBM,
+    one CUDA graph per step, three blocks of K steps (median block reported)."""
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.trainer import Trainer
+    pname, over, n_rays, desc = WORKLOADS[wl_name]
+    cfg, kind = preset(pname, **over)
+    torch.manual_seed(cfg.experiment.randomseed)
+    model = getattr(M, cfg.nerf.type)(cfg)
+    model.to(dev)
+    for net in {id(model.coarse): model.coarse, id(model.fine): model.fine}.values():
+        net.mlp_mode = args.mlp_mode
+    trainer = Trainer(model, distributed=world > 1, use_graph=not args.no_graph)
+    torch.manual_seed(4321 + rank)
+    host = make_batches(kind, n_rays, 4, rank, cfg.dataset.near, cfg.dataset.far)
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def block(count):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(count):
+            trainer.step(*resident[s % len(resident)])
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    block(max(W, Trainer.GRAPH_WARMUP + 2))
+    blocks = sorted(block(K) for _ in range(3))
+    ms = blocks[1]
+    flops = mlp_flops_per_step(cfg, n_rays)
+    out = {"metric": "train_rays_per_sec", "value": n_rays * world * K / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / K,
+           "scaling": "weak", "workload": desc, "rays_per_gpu": n_rays, "steps": K,
+           "spread_ms_per_step": [b / K for b in blocks],
+           "mlp_tflops_over_whole_step": flops / (ms / K * 1e-3) / 1e12,
+           "nccl_in_graph": bool(world > 1 and trainer.use_graph and trainer._graph_tail is None)}
+    del trainer, model, resident
+    torch.cuda.empty_cache()
+    return out
+
+
 _JSON_OUT = None
 
 
@@ -374,6 +425,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame render leg (configs[2])")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the DDNeRF 16,384 rays/GPU training block (configs[3])")
     ap.add_argument("--render-frames", type=int, default=5)
     ap.add_argument("--render-chunk", type=int, default=0, help="rays per chunk of the render leg (0: one chunk per rank)")
     args = ap.parse_args()
@@ -620,6 +672,8 @@ def main():
         per_row = ((0.244e9 + 2.650e9) + (0.175e9 + 2.558e9) + (5.810e9 + 0.009e9)) / 524288.0
         line["roofline"]["traffic"] = per_row * rows_step if args.mlp_mode == "bf16" else None
         line["roofline"]["traffic_note"] = "dram__bytes_read+write of fwd/dx/dw from profiles/r01b_ncu_mlp_tc_*.md, per step"
+    if not args.no_cfg4 and args.workload != "cfg4":
+        line["train_cfg4"] = run_train_block(args, "cfg4", dev, world, rank, dist, K, W)
     if not args.no_render:
         line["render"] = run_render(args, dev, world, rank, dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

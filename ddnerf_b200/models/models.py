@@ -76,7 +76,8 @@ class GeneralMipNerfModel(torch.nn.Module):
         if not self.randoms or self.randoms.get(key) is None:
             return None
         lo, hi = getattr(self, "_chunk_rows", (0, None))
-        return self.randoms[key][lo:hi]
+        base = getattr(self, "_rand_base", 0)              # row offset of this run_iter call inside the injected tensors
+        return self.randoms[key][base + lo: None if hi is None else base + hi]
 
     def _mode_cfg(self, mode):
         return getattr(self.cfg.nerf, mode)

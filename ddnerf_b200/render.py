@@ -3,8 +3,8 @@
     camera pose -> rays (csrc/raygen.cu) -> model.run_iter(mode="validation") -> 8-bit images (csrc/frame.cu)
 
 Rows f1 and f4 of SURVEY.md section 8f around the per-ray path.  ``FrameRenderer`` owns the static buffers of one
-frame size and, with ``use_graph=True``, replays the whole frame as ONE CUDA graph (with several ranks: two graphs
-around the one eagerly launched NCCL all-reduce that makes the disparity range a whole-frame range): the only host->device traffic
+frame size and, with ``use_graph=True``, replays the whole frame as ONE CUDA graph (with several ranks the graph contains
+the one NCCL all-reduce that makes the disparity range a whole-frame range): the only host->device traffic
 of a frame is its 48-byte pose, the only device->host traffic the 8-bit images (4 bytes per pixel, 6 with the
 side-by-side video frame) instead of 28 bytes of rays in and 16 bytes of float images out per pixel.
 """
@@ -75,7 +75,8 @@ class FrameRenderer:
         # the render loop never reads them
         model.record_distributions = False
         self.use_graph = bool(use_graph)
-        self._graph = None           # one GPU: the whole frame; several ranks: the part before the collective
+        self.capture_collective = True   # several ranks: capture the NCCL all-reduce into the frame's graph (one graph per frame)
+        self._graph = None           # the whole frame (or, when the collective cannot be captured, the part before it)
         self._graph_tail = None      # several ranks: the part after it
         self._calls = 0
         self.float_out = None
@@ -136,13 +137,24 @@ class FrameRenderer:
                         st.dirty = True
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    if self.world == 1:
-                        self._body()
-                    else:
+                one_graph = self.world == 1 or self.capture_collective
+                try:
+                    with torch.cuda.graph(g):
+                        if one_graph:
+                            self._body()                     # several ranks: the NCCL MAX all-reduce is a node of the graph
+                        else:
+                            self._head()
+                except Exception:
+                    if not (self.world > 1 and one_graph):
+                        raise
+                    # this NCCL / driver combination refuses to capture the collective: two graphs around an eager call
+                    self.capture_collective, one_graph = False, False
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
                         self._head()
                 self._graph = g
-                if self.world > 1:                           # the NCCL call stays eager, between two graphs
+                if not one_graph:                            # the NCCL call stays eager, between two graphs
                     t = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(t, pool=g.pool()):
                         self._tail()

@@ -265,6 +265,7 @@ class Trainer:
         loss = mse = None
         for lo, hi in spans:
             frac = (hi - lo) / N
+            self.model._rand_base = lo                           # (injected random tensors of the parity tests: this chunk's rows)
             out = self.model.run_iter(ro[lo:hi], rd[lo:hi], rad[lo:hi], mode="train", rgb_target=tgt[lo:hi])
             mse_c, g0, g1 = ops.mse_loss_and_grad(out[0]["rgb"], out[1]["rgb"], tgt[lo:hi], coef[0] * frac, coef[1] * frac)
             loss_c = (coef[0] * frac) * mse_c[0] + (coef[1] * frac) * mse_c[1]
@@ -279,6 +280,7 @@ class Trainer:
             del out, tensors, grads                              # the chunk's saved activations go back to the allocator
             loss = loss_c if loss is None else loss + loss_c
             mse = mse_c * frac if mse is None else mse + mse_c * frac
+        self.model._rand_base = 0
         for b in self.buckets:
             b.gather_grads()
         if hyper is not None and self.distributed and self.world > 1 and not collective_inside:
@@ -361,13 +363,29 @@ class Trainer:
         if isinstance(saved, torch.Tensor):
             saved = float(saved)
         nccl_in_graph = self.distributed and self.world > 1 and self.capture_collective
+
+        def record(g, inside):
+            try:
+                with torch.cuda.graph(g):
+                    self._schedule_dev()
+                    tp.gaussian_smooth_factor = smooth_dev if self.is_dd else saved
+                    return self._body(*self._static["in"], lr, hyper=self._hyper_dev, collective_inside=inside)
+            finally:
+                tp.gaussian_smooth_factor = saved
+
         try:
-            with torch.cuda.graph(graph):
-                self._schedule_dev()
-                tp.gaussian_smooth_factor = smooth_dev if self.is_dd else saved
-                loss, mse = self._body(*self._static["in"], lr, hyper=self._hyper_dev, collective_inside=nccl_in_graph)
-        finally:
-            tp.gaussian_smooth_factor = saved
+            loss, mse = record(graph, nccl_in_graph)
+        except Exception:
+            if not nccl_in_graph:
+                raise
+            # this NCCL / driver combination refuses to capture the collective: two graphs around an eager all-reduce
+            self.capture_collective = nccl_in_graph = False
+            for b in self.buckets:
+                for p in b.params:
+                    p.grad = None
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            loss, mse = record(graph, False)
         self._static["loss"], self._static["mse"] = loss, mse
         self._graph_tail = None
         if self.distributed and self.world > 1 and not nccl_in_graph:   # the collective launched eagerly between two graphs

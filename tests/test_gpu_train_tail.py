@@ -249,3 +249,49 @@ def test_trainer_checkpoint_resume_continues_the_trajectory():
     assert [x.step for x in c.buckets] == [8, 8] and c.iter == 8
     assert (wa - wc).abs().max().item() < 2e-3
     assert torch.nn.functional.cosine_similarity((wa - wa.mean()).double(), (wc - wc.mean()).double(), dim=0).item() > 0.99999
+
+
+@pytest.mark.parametrize("pname", ["config_blender_mipnerf", "config_blender"])
+def test_gradient_accumulation_over_ray_chunks(pname):
+    """A batch above cfg.nerf.train.chunksize: backward per chunk into the flat gradient bucket (Trainer.accumulate_chunks)
+    gives the gradient, the loss and the weight update of the reference's order -- every chunk forward (models.py:53,160),
+    one backward over all of them (train_model.py:170) -- while only one chunk's saved activations are alive at a time.
+    700 rays in chunks of 256 (ragged last chunk), DDNeRF (blender row filter, per-chunk dp-loss means) and mip-NeRF."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    from ddnerf_b200.trainer import Trainer
+    dev = torch.device(DEV)
+    N, s0, s1 = 700, 16, 16
+    ro, rd, rad, near, far = synth_rays("blender", N, seed=6)
+    g = torch.Generator().manual_seed(3)
+    target = torch.rand(N, 3, generator=g)
+    rnd = dict(t_rand=torch.rand(N, s0 + 1, generator=g), noise0=torch.randn(N, s0, generator=g),
+               u_rand=torch.rand(N, s1 + 1, generator=g), noise1=torch.randn(N, s1, generator=g))
+    res = []
+    for accumulate in (False, True):
+        cfg, _ = preset(pname, num_coarse=s0, num_fine=s1)
+        cfg.nerf.train.chunksize = 256
+        is_dd = cfg.nerf.type == "DDNerfModel"
+        model = getattr(M, cfg.nerf.type)(cfg)
+        model.coarse.load_state_dict(orc.init_mlp_params(is_dd, seed=21))
+        model.coarse.mlp_mode = "bf16"
+        if is_dd:
+            model.fine.load_state_dict(orc.init_mlp_params(False, seed=22))
+            model.fine.mlp_mode = "bf16"
+        model.to(dev)
+        model.randoms = {k: v.to(dev) for k, v in rnd.items()}
+        tr = Trainer(model, train_iters=100, use_graph=False)
+        tr.accumulate_chunks = accumulate
+        torch.cuda.reset_peak_memory_stats()
+        loss, mse = tr.step(*[t.to(dev) for t in (ro, rd, rad, target)])
+        torch.cuda.synchronize()
+        res.append((loss.item(), mse.cpu(), torch.cat([b.grad.clone() for b in tr.buckets]).cpu(),
+                    torch.cat([b.flat.clone() for b in tr.buckets]).cpu(), torch.cuda.max_memory_allocated()))
+    (l0, m0, g0, w0, mem0), (l1, m1, g1, w1, mem1) = res
+    assert abs(l0 - l1) < 1e-5 and (m0 - m1).abs().max().item() < 1e-6
+    assert ((g0 - g1).abs().max() / g0.abs().max()).item() < 1e-4           # fp32 accumulation order only
+    assert torch.nn.functional.cosine_similarity(g0.double(), g1.double(), dim=0).item() > 0.9999999
+    assert (w0 - w1).abs().max().item() < 1e-4
+    assert mem1 < mem0                                                      # one chunk's saves instead of three

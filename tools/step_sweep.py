@@ -7,8 +7,9 @@ events after warm-up; reported as rays/s and as MLP throughput against the measu
 
     python tools/step_sweep.py [--out profiles/r01b_step_sweep] [--steps 10] [--max-rows 2200000]
 
-Points whose saved activations would not fit (rows per pass above --max-rows; the reference chunks the forward
-but keeps every chunk's autograd state until backward, and so does this path) are listed as skipped.
+Points whose saved activations would not fit in one piece (rows per pass above --max-rows) run with the batch split
+into ray chunks of cfg.nerf.train.chunksize and the backward of each chunk right after its forward (gradient
+accumulation, Trainer.accumulate_chunks) -- the `chunks` column.
 """
 import argparse
 import json
@@ -67,11 +68,11 @@ def main():
                 cfg, kind = preset(pname, num_coarse=s, num_fine=s)
                 name = "DDNeRF" if cfg.nerf.type == "DDNerfModel" else "mip-NeRF"
                 rec = dict(model=name, rays=n_rays, samples=2 * s)
-                if n_rays * s > args.max_rows:
-                    rec["skipped"] = f"{n_rays * s} rows per pass: saved activations exceed the budget"
-                    rows.append(rec)
-                    continue
-                cfg.nerf.train.chunksize = n_rays
+                chunk = n_rays
+                while chunk * s > args.max_rows:                 # saved activations of one chunk: 5.4 KB per row and pass
+                    chunk //= 2
+                rec["chunks"] = n_rays // chunk
+                cfg.nerf.train.chunksize = chunk
                 try:
                     ms = time_point(cfg, kind, n_rays, dev, args.steps)
                 except torch.OutOfMemoryError:
@@ -89,12 +90,12 @@ def main():
     with open(args.out + ".md", "w") as f:
         f.write("# Training-step sweep (BASELINE.json configs[4]), one B200, bf16 MLP, one CUDA graph per step\n\n")
         f.write(f"MLP column: algorithmic MLP FLOPs of the step / WHOLE step time, against {peak} TFLOP/s (measured sustained bf16)\n\n")
-        f.write("| model | rays | samples/ray (coarse+fine) | ms/step | rays/s | MLP TFLOP/s over the whole step | of peak |\n|---|---:|---:|---:|---:|---:|---:|\n")
+        f.write("| model | rays | samples/ray (coarse+fine) | ray chunks | ms/step | rays/s | MLP TFLOP/s over the whole step | of peak |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
             if "skipped" in r:
-                f.write(f"| {r['model']} | {r['rays']} | {r['samples']} | — | — | — | skipped: {r['skipped']} |\n")
+                f.write(f"| {r['model']} | {r['rays']} | {r['samples']} | {r.get('chunks', 1)} | — | — | — | skipped: {r['skipped']} |\n")
             else:
-                f.write(f"| {r['model']} | {r['rays']} | {r['samples']} | {r['ms_per_step']:.3f} | {r['rays_per_s']:.0f} | "
+                f.write(f"| {r['model']} | {r['rays']} | {r['samples']} | {r.get('chunks', 1)} | {r['ms_per_step']:.3f} | {r['rays_per_s']:.0f} | "
                         f"{r['mlp_tflops_whole_step']:.0f} | {100 * r['frac_of_sustained_peak']:.1f} % |\n")
 
 
