@@ -56,6 +56,7 @@ SIGNATURES = {
     "ddnerf_mlp_tc_backward_dx": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_p]),
     "ddnerf_mlp_tc_backward_dw": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(MlpPtrs), c_l, c_i, c_i, c_p]),
     "ddnerf_mlp_tc_program_check": (c_i, []),
+    "ddnerf_mlp_tc_set_pair_mode": (c_i, [c_i]),
     "ddnerf_mlp_tc_set_profile_buffer": (c_i, [c_p]),
     "ddnerf_mlp_tc_dw_set_profile_buffer": (c_i, [c_p]),
     "ddnerf_mlp_tc_dw_plan": (c_i, [c_l, c_i, ctypes.POINTER(ctypes.c_uint32), c_i]),

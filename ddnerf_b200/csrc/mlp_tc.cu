@@ -27,6 +27,8 @@
 // then dZ_feat = [dZ_dir | g_density] . [W_dir[:, :256] ; w_alpha], dZ_l = (dZ_{l+1} . W_{l+1}) *
 // relu'_l down to layer 0, with transposed weight stages.  Every dZ tile image is stored for the
 // weight-gradient kernel (mlp_tc_dw.cu).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -65,6 +67,17 @@ struct ChainArgs {
 };
 
 __device__ __forceinline__ unsigned long long clk() { return clock64(); }
+
+// The work-unit loop of a CTA and the tile numbering, for both kernel variants.  Single CTA: a unit is a 256-row item
+// (tiles 2 unit + T).  CTA pair: a unit is 512 rows = two super-tiles, tile (2 unit + T) * 2 + rank; a unit may reach
+// past the allocated tiles (odd item count) -- such a tile is computed on zeros and neither stored nor read.
+struct Topo {
+    int first, step, n_units;
+    int pair, rank;
+    int n_tiles;                    // allocated 128-row tiles (2 per 256-row item)
+    uint32_t act_ready_leader;      // pair: shared::cluster address of the leader's act_ready[0]
+    __device__ __forceinline__ int tile(int unit, int T) const { return pair ? (2 * unit + T) * 2 + rank : unit * 2 + T; }
+};
 
 // descriptor high words: K-major SWIZZLE_128B act buffer (SBO = 8 rows x 128 B), SWIZZLE_64B ring stages
 constexpr uint32_t kHi128 = (uint32_t)(tc::smem_desc(0, 0, 1024, tc::LAYOUT_SW128) >> 32);
@@ -126,7 +139,9 @@ __device__ __forceinline__ uint32_t epi_chunk32(const uint32_t (&v)[32], const f
     return ~neg;
 }
 
-__device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+__device__ __forceinline__ void signal_act_ready(const Topo& tp, SmemCtl* ctl, int T);
+
+__device__ void epilogue_fwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
     const Program& P = c_prog[0];
     const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane, tid = warp * 32 + lane;
     const uint32_t tmem_q = ctl->tmem_base + ((uint32_t)(q * 32) << 16);
@@ -140,14 +155,15 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
 
     ctl->bias[0][tid] = __ldg(g.bias + P.epis[0].bias_off + tid);          // bias of the first epilogue
     named_bar(1, kEpiThreads);
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+    for (int unit = tp.first; unit < tp.n_units; unit += tp.step) {
         for (int e = 0; e < n_epis; ++e, ++k) {
             const Epi E = P.epis[e];
             const float* bias_s = ctl->bias[k & 1];
             const float nb = __ldg(g.bias + P.epis[(e + 1 == n_epis) ? 0 : e + 1].bias_off + tid);
 #pragma unroll 1
             for (int T = 0; T < 2; ++T) {
-                const int tile_g = item * 2 + T;
+                const int tile_g = tp.tile(unit, T);
+                const bool tile_ok = tile_g < n_tiles;
                 const int64_t row_g = (int64_t)tile_g * 128 + row;
                 const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
                 const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
@@ -204,7 +220,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                         tc::tmem_ld_wait();
                         if (row_g < g.rows) g.out[row_g * g.C + 3] = __uint_as_float(v[0]) + bias_s[128];
                     }
-                    if (g.mask && E.save_layer >= 0 && E.relu) {
+                    if (g.mask && E.save_layer >= 0 && E.relu && tile_ok) {
                         uint32_t* mp = g.mask + (((size_t)E.save_layer * n_tiles + tile_g) * 128 + row) * 8;
                         if (E.mode == EPI_DIR) {                           // words 0..1 / 2..3 of the 128 view-branch columns
                             *reinterpret_cast<uint2*>(mp + 2 * hf) = make_uint2(mk[0], mk[1]);
@@ -234,13 +250,14 @@ __device__ void epilogue_fwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                 if (T == 1) ctl->bias[(k + 1) & 1][tid] = nb;      // (the other buffer: nobody reads it now)
                 named_bar(1, kEpiThreads);
                 if (tid == 0) {
-                    tc::mbar_arrive(&ctl->act_ready[T]);
+                    signal_act_ready(tp, ctl, T);
                     if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     if (g.save && E.save_layer >= 0) {
                         const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
-                        tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
-                                          E.save_bytes, pol_stream);
-                        tc::bulk_commit();
+                        if (tile_ok)
+                            tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
+                                              E.save_bytes, pol_stream);
+                        tc::bulk_commit();          // (an empty group for a tile past the end keeps the alternation of the waits)
                         ++stores;
                     }
                 }
@@ -274,7 +291,7 @@ __device__ __forceinline__ void bwd_chunk32(const uint32_t (&v)[32], uint32_t m,
     store_chunk32(act_u32, row, c0, pk);
 }
 
-__device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
+__device__ void epilogue_bwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, uint8_t* act_all, int warp, int lane) {
     const Program& P = c_prog[1];
     const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane, tid = warp * 32 + lane;
     const uint32_t tmem_q = ctl->tmem_base + ((uint32_t)(q * 32) << 16);
@@ -285,18 +302,19 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
     const uint64_t pol_stream = tc::l2_policy_evict_first();
     unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+    for (int unit = tp.first; unit < tp.n_units; unit += tp.step) {
         for (int e = 0; e < n_epis; ++e) {
             const Epi E = P.epis[e];
 #pragma unroll 1
             for (int T = 0; T < 2; ++T) {
-                const int tile_g = item * 2 + T;
+                const int tile_g = tp.tile(unit, T);
+                const bool tile_ok = tile_g < n_tiles;
                 const int64_t row_g = (int64_t)tile_g * 128 + row;
                 const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
                 const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
                 const unsigned long long tw0 = g.prof ? clk() : 0;
                 uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                if (E.mask_layer >= 0) {                 // this half's ReLU mask words (view branch: 2 words per half)
+                if (E.mask_layer >= 0 && tile_ok) {      // this half's ReLU mask words (view branch: 2 words per half)
                     const uint32_t* mp = g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8;
                     if (E.mode == EPI_BWD_IN) {
                         const uint2 m = __ldg(reinterpret_cast<const uint2*>(mp + 2 * hf));
@@ -379,11 +397,12 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
                 tc::fence_proxy_async_smem();
                 named_bar(1, kEpiThreads);
                 if (tid == 0) {
-                    if (E.signal) tc::mbar_arrive(&ctl->act_ready[T]);
+                    if (E.signal) signal_act_ready(tp, ctl, T);
                     if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
-                    tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes, E.save_bytes,
-                                      pol_stream);
+                    if (tile_ok)
+                        tc::bulk_s2g_hint(g.save + ((size_t)E.save_layer * n_tiles + tile_s) * kActBytes, act_all + T * kActBytes,
+                                          E.save_bytes, pol_stream);
                     tc::bulk_commit();
                     ++stores;
                 }
@@ -396,6 +415,13 @@ __device__ void epilogue_bwd(const ChainArgs& g, SmemCtl* ctl, uint8_t* act_all,
         o[3] = t_wait; o[4] = t_busy; o[5] = n_epi;
         o[6] = t_pre; o[7] = t_work;
     }
+}
+
+// the epilogue of (unit, T) is complete: the act buffer holds the next A operand, the accumulator is drained.
+// Pair: both CTAs arrive on the leader's barrier (count 2), released at cluster scope.
+__device__ __forceinline__ void signal_act_ready(const Topo& tp, SmemCtl* ctl, int T) {
+    if (tp.pair) tc::mbar_arrive_cluster_addr(tp.act_ready_leader + (uint32_t)T * 8u);
+    else tc::mbar_arrive(&ctl->act_ready[T]);
 }
 
 template <int PI>
@@ -540,10 +566,10 @@ __device__ void mma_role(const ChainArgs& g, SmemCtl* ctl, uint32_t smem_base) {
     }
 }
 
-__device__ void encoder_role(const ChainArgs& g, SmemCtl* ctl, int tid);
+__device__ void encoder_role(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, int tid);
 
 template <int PI>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainArgs g) {
+__global__ void __launch_bounds__(PI == 0 ? kThreads : kThreads - kEncThreads, 1) mlp_tc_chain_kernel(const ChainArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* act_all = smem;
     uint8_t* ring = smem + kRingOff;
@@ -564,20 +590,331 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_chain_kernel(const ChainAr
     __syncthreads();
     tc::tc_fence_after_sync();
 
+    const Topo tp{(int)blockIdx.x, (int)gridDim.x, g.n_items, 0, 0, g.n_items * 2, 0u};
     if (warp < 8) {
-        if (PI == 0) epilogue_fwd(g, ctl, act_all, warp, lane);
-        else epilogue_bwd(g, ctl, act_all, warp, lane);
+        if (PI == 0) epilogue_fwd(g, tp, ctl, act_all, warp, lane);
+        else epilogue_bwd(g, tp, ctl, act_all, warp, lane);
     } else if (warp == 8) {
         if (lane == 0) producer_role<PI>(g, ctl, ring);
     } else if (warp == 9) {
         mma_role<PI>(g, ctl, tc::smem_u32(smem));
     } else {
-        if (PI == 0 && g.enc_mode) encoder_role(g, ctl, (int)threadIdx.x - 320);
+        if (PI == 0 && g.enc_mode) encoder_role(g, tp, ctl, (int)threadIdx.x - 320);
     }
 
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(ctl->tmem_base, 512);
+}
+
+// ---- CTA-pair variant (cta_group::2), see mlp_tc.cuh ------------------------------------------------------------
+__constant__ PProgram c_pprog[2];
+
+struct __align__(64) PairMaps { CUtensorMap m[kPairMaps]; };       // PM_W128, PM_W72, PM_W8 over the packed weights; PM_ENC over the images
+
+// Stage order of one unit (all three roles walk it): for every epilogue e, for super-tile T in {0, 1}: the stages of e.
+// The whole warp walks the table (uniform control flow, uniform constant loads); one elected lane issues the copies.
+template <int PI>
+__device__ void producer_pair(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, uint8_t* ring, const PairMaps& maps) {
+    const PProgram& P = c_pprog[PI];
+    const uint64_t pol_w = tc::l2_policy_evict_last(), pol_in = tc::l2_policy_evict_first();
+    const uint32_t full_leader = tc::mapa_u32(tc::smem_u32(&ctl->full[0]), 0);
+    const uint32_t full_own = tc::smem_u32(&ctl->full[0]), empty0 = tc::smem_u32(&ctl->empty[0]);
+    const uint32_t ring_u32 = tc::smem_u32(ring);
+    const uint32_t rank = (uint32_t)tp.rank;
+    uint32_t slot = 0, phase = 0, n = 0;
+    const bool prof = g.prof != nullptr && tp.rank == 1;          // the peer's producer reports (its issuer slots are free)
+    unsigned long long t_empty = 0, t_enc = 0;
+    const unsigned long long t_begin = clk();
+    for (int unit = tp.first; unit < tp.n_units; unit += tp.step, ++n) {
+        if (PI == 0 && g.enc_mode) {                                // this CTA's encoder warps wrote its blocks
+            const unsigned long long t0 = prof ? clk() : 0;
+            tc::mbar_wait(&ctl->enc_ready[n & 1u], (n >> 1) & 1u);
+            if (prof) t_enc += clk() - t0;
+        }
+        for (int e = 0; e < P.n_phases; ++e) {
+            const int s1 = P.phase_begin[e + 1];
+            const uint32_t fast = P.phase_fast[e];
+            if (fast) {                 // plain layer: four stages of two N = 256 chunks each, once (shared) or per super-tile
+                const uint32_t idx0 = P.phase_idx0[e] + rank;
+                for (uint32_t T = 0; T < (fast == 2 ? 1u : 2u); ++T) {
+#pragma unroll
+                    for (uint32_t st = 0; st < 4; ++st) {
+                        {
+                            const unsigned long long t0 = prof ? clk() : 0;
+                            tc::mbar_wait_u32(empty0 + slot * 8u, phase ^ 1u);
+                            if (prof) t_empty += clk() - t0;
+                        }
+                        if (tc::elect_one()) {
+                            if (rank == 0) {
+                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_own + slot * 8u), "r"(32768u) : "memory");
+                            }
+                            tc::tma_load_3d_pair(ring_u32 + slot * kSlotBytes, &maps.m[PM_W128], 0, 0, (int)(idx0 + 4u * st), full_leader + slot * 8u, pol_w);
+                        }
+                        __syncwarp();
+                        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+                    }
+                }
+                continue;
+            }
+            for (int s = P.phase_begin[e]; s < s1;) {
+                // a group: up to two shared stages (loaded once), or a run of stages of one super-tile (loaded for T0, then for T1)
+                const bool shared = (P.st[s].flags & PF_SHARED) != 0;
+                int ge = s + 1;
+                if (shared) { if (ge < s1 && (P.st[ge].flags & PF_SHARED)) ++ge; }
+                else { while (ge < s1 && !(P.st[ge].flags & PF_SHARED)) ++ge; }
+                for (int T = 0; T < (shared ? 1 : 2); ++T) {
+                    // image holding this CTA's encoded blocks of super-tile T (8 blocks of 8 KB each), and which tile of it they are
+                    const uint32_t enc_blk0 = (g.enc_mode == 2 ? (blockIdx.x * 2u + (n & 1u)) : (uint32_t)(2 * unit + T)) * 8u;
+                    const uint32_t tsel = g.enc_mode == 2 ? (uint32_t)T : rank;
+                    for (int j = s; j < ge; ++j) {
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(&P.st[j]);
+                        const uint4 q1 = *(reinterpret_cast<const uint4*>(&P.st[j]) + 1);       // the two copies
+                        const uint32_t n_copies = (q0.y >> 8) & 0xFFu;
+                        {
+                            const unsigned long long t0 = prof ? clk() : 0;
+                            tc::mbar_wait_u32(empty0 + slot * 8u, phase ^ 1u);
+                            if (prof) t_empty += clk() - t0;
+                        }
+                        if (tc::elect_one()) {
+                            if (rank == 0) {
+                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_own + slot * 8u), "r"(q0.w) : "memory");
+                            }
+                            const uint32_t dst = ring_u32 + slot * kSlotBytes, bar = full_leader + slot * 8u;
+                            {
+                                const uint32_t mul = q1.y & 0xFFu, map = (q1.y >> 8) & 0xFFu, off = q1.y >> 16;
+                                const bool is_enc = map == PM_ENC;
+                                const uint32_t idx = q1.x + (is_enc ? tsel * mul + enc_blk0 : rank);
+                                tc::tma_load_3d_pair(dst + off, &maps.m[map], 0, 0, (int)idx, bar, is_enc ? pol_in : pol_w);
+                            }
+                            if (n_copies > 1) {
+                                const uint32_t map = (q1.w >> 8) & 0xFFu, off = q1.w >> 16;      // the second copy is always a weight chunk
+                                tc::tma_load_3d_pair(dst + off, &maps.m[map], 0, 0, (int)(q1.z + rank), bar, pol_w);
+                            }
+                        }
+                        __syncwarp();
+                        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+                    }
+                }
+                s = ge;
+            }
+        }
+    }
+    if (prof && (threadIdx.x & 31) == 0) {
+        unsigned long long* o = g.prof + (size_t)blockIdx.x * 8;
+        o[0] = clk() - t_begin; o[1] = t_empty; o[2] = t_enc;      // producer: total / waiting for free slots / for the encoder
+    }
+}
+
+// MMA issuer of the pair (leader CTA).  The whole warp walks the program (uniform control flow keeps descriptors and barrier
+// addresses in uniform registers, where tcgen05.mma wants them); one elected lane issues.  The regular layers (a K = 256,
+// N = 256 accumulation over the act buffer: four two-chunk stages, 16 MMAs) run through a straight-line path with
+// compile-time operand offsets.
+struct PairIssuer {
+    uint32_t base16, tmem, full0, empty0, acc0, act0;
+    uint32_t slot, phase, act_phase;
+    unsigned long long t_act, t_stage;
+    bool prof;
+
+    __device__ __forceinline__ void wait_act(uint32_t T) {            // both CTAs' epilogues of this super-tile are done
+        const unsigned long long t0 = prof ? clk() : 0;
+        tc::mbar_wait_u32(act0 + T * 8u, (act_phase >> T) & 1u);
+        act_phase ^= 1u << T;
+        if (prof) t_act += clk() - t0;
+    }
+    __device__ __forceinline__ void wait_stage() {                    // the current stage has landed in BOTH CTAs
+        const unsigned long long t0 = prof ? clk() : 0;
+        tc::mbar_wait_u32(full0 + slot * 8u, phase);
+        if (prof) t_stage += clk() - t0;
+    }
+    __device__ __forceinline__ void advance() {
+        if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+    }
+};
+
+template <int PI>
+__device__ void mma_pair(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, uint32_t smem_base) {
+    const PProgram& P = c_pprog[PI];
+    PairIssuer S;
+    S.base16 = smem_base >> 4;
+    S.tmem = ctl->tmem_base;
+    S.full0 = tc::smem_u32(&ctl->full[0]);
+    S.empty0 = tc::smem_u32(&ctl->empty[0]);
+    S.acc0 = tc::smem_u32(&ctl->acc_full[0]);
+    S.act0 = tc::smem_u32(&ctl->act_ready[0]);
+    S.slot = S.phase = S.act_phase = 0;
+    S.t_act = S.t_stage = 0;
+    S.prof = g.prof != nullptr;
+    const uint32_t encf0 = tc::smem_u32(&ctl->enc_free[0]);
+    const uint32_t ring16 = S.base16 + (kRingOff >> 4);
+    const uint32_t idesc256 = tc::idesc_bf16(256, 256, 0, 0);
+    const unsigned long long t_begin = clk();
+    uint32_t n = 0;
+    // the four K = 16 MMAs of a two-chunk stage of a plain layer: act chunks 2 st, 2 st + 1 against the two weight chunks in `slot`
+    auto layer_stage = [&](uint32_t T, int st, uint32_t slot) {
+        const uint32_t d = S.tmem + T * 256u;
+        const uint64_t a = ((uint64_t)kHi128 << 32) | (uint64_t)(S.base16 + T * (kActBytes >> 4) + (uint32_t)st * 1024u);
+        const uint64_t b = ((uint64_t)kHi64 << 32) | (uint64_t)(ring16 + slot * (kSlotBytes >> 4));
+        tc::mma2_f16_ss(d, a, b, idesc256, st == 0 ? 0u : 1u);
+        tc::mma2_f16_ss(d, a + 2, b + 2, idesc256, 1u);
+        tc::mma2_f16_ss(d, a + 4, b + 512, idesc256, 1u);
+        tc::mma2_f16_ss(d, a + 6, b + 514, idesc256, 1u);
+    };
+    for (int unit = tp.first; unit < tp.n_units; unit += tp.step, ++n) {
+        for (int e = 0; e < P.n_phases; ++e) {
+            const int s0 = P.phase_begin[e], s1 = P.phase_begin[e + 1];
+            if (s0 == s1) continue;
+            const uint32_t fast = P.phase_fast[e];
+            if (fast == 2) {            // plain layer, shared stages: [T0: st 0, 1] [T1: st 0, 1] [T0: st 2, 3] [T1: st 2, 3]
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t sa = S.slot;
+                    S.advance();
+                    const uint32_t sb = S.slot;
+                    if (h == 0) S.wait_act(0);
+                    {
+                        const unsigned long long t0 = S.prof ? clk() : 0;
+                        tc::mbar_wait_u32(S.full0 + sa * 8u, sb == 0 ? S.phase ^ 1u : S.phase);      // (the phase bit flips when the slot index wraps)
+                        if (S.prof) S.t_stage += clk() - t0;
+                    }
+                    tc::tc_fence_after_sync();
+                    if (tc::elect_one()) layer_stage(0, 2 * h, sa);
+                    __syncwarp();
+                    S.wait_stage();                                                                // slot sb
+                    tc::tc_fence_after_sync();
+                    if (tc::elect_one()) {
+                        layer_stage(0, 2 * h + 1, sb);
+                        if (h == 1) tc::mma2_commit_u32(S.acc0);
+                    }
+                    __syncwarp();
+                    if (h == 0) S.wait_act(1);
+                    tc::tc_fence_after_sync();
+                    if (tc::elect_one()) {
+                        layer_stage(1, 2 * h, sa);
+                        tc::mma2_commit_u32(S.empty0 + sa * 8u);                                   // frees the slot in both CTAs
+                        layer_stage(1, 2 * h + 1, sb);
+                        tc::mma2_commit_u32(S.empty0 + sb * 8u);
+                        if (h == 1) tc::mma2_commit_u32(S.acc0 + 8u);
+                    }
+                    __syncwarp();
+                    S.advance();
+                }
+                continue;
+            }
+            if (fast == 1) {            // plain layer, stages per super-tile
+                for (uint32_t T = 0; T < 2; ++T) {
+                    S.wait_act(T);
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        S.wait_stage();
+                        tc::tc_fence_after_sync();
+                        if (tc::elect_one()) {
+                            layer_stage(T, st, S.slot);
+                            tc::mma2_commit_u32(S.empty0 + S.slot * 8u);
+                            if (st == 3) tc::mma2_commit_u32(S.acc0 + T * 8u);
+                        }
+                        __syncwarp();
+                        S.advance();
+                    }
+                }
+                continue;
+            }
+            for (int s = s0; s < s1;) {
+                const bool shared = (P.st[s].flags & PF_SHARED) != 0;
+                int ge = s + 1;
+                if (shared) { if (ge < s1 && (P.st[ge].flags & PF_SHARED)) ++ge; }
+                else { while (ge < s1 && !(P.st[ge].flags & PF_SHARED)) ++ge; }
+                const uint32_t slot_g = S.slot, phase_g = S.phase;       // ring position of the group's first stage
+                for (uint32_t T = 0; T < 2; ++T) {
+                    const uint32_t d = S.tmem + T * 256u;
+                    const uint32_t act16 = S.base16 + T * (kActBytes >> 4);
+                    if (shared) { S.slot = slot_g; S.phase = phase_g; }  // T1 walks the same slots again
+                    for (int j = s; j < ge; ++j) {
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(&P.st[j]);      // kind..flags | a_chunk0, n_copies, b_stride | idesc | tx
+                        const uint32_t kind = q0.x & 0xFFu, n_chunks = (q0.x >> 8) & 0xFFu, last_nk16 = (q0.x >> 16) & 0xFFu, flags = q0.x >> 24;
+                        const uint32_t a_chunk0 = q0.y & 0xFFu, b_stride16 = (q0.y >> 16) >> 4, idesc = q0.z;
+                        if ((flags & PF_WAIT_ACT) || ((flags & PF_WAIT_PREV) && n > 0)) S.wait_act(T);
+                        if (!shared || T == 0) S.wait_stage();
+                        tc::tc_fence_after_sync();
+                        if (tc::elect_one()) {
+                            const uint32_t slot16 = ring16 + S.slot * (kSlotBytes >> 4);
+#pragma unroll 1
+                            for (uint32_t c = 0; c < n_chunks; ++c) {
+                                uint64_t a, b;
+                                if (kind == PS_ENCW) {
+                                    a = ((uint64_t)kHi64 << 32) | (uint64_t)slot16;
+                                    b = ((uint64_t)kHi64 << 32) | (uint64_t)(slot16 + (8192u >> 4));
+                                } else {
+                                    const uint32_t ch = a_chunk0 + c;
+                                    a = ((uint64_t)kHi128 << 32) | (uint64_t)(act16 + (ch >> 1) * 1024u + (ch & 1u) * 4u);
+                                    b = ((uint64_t)kHi64 << 32) | (uint64_t)(slot16 + c * b_stride16);
+                                }
+                                tc::mma2_f16_ss(d, a, b, idesc, ((flags & PF_FIRST) && c == 0) ? 0u : 1u);
+                                if (c + 1 < n_chunks || last_nk16 > 1) tc::mma2_f16_ss(d, a + 2, b + 2, idesc, 1u);
+                            }
+                            if (!shared || T == 1) tc::mma2_commit_u32(S.empty0 + S.slot * 8u);
+                            if (flags & PF_COMMIT_ACC) tc::mma2_commit_u32(S.acc0 + T * 8u);
+                            if (PI == 0 && (flags & PF_ENC_DONE) && T == 1) tc::mma2_commit_u32(encf0 + (n & 1u) * 8u);
+                        }
+                        __syncwarp();
+                        S.advance();
+                    }
+                }
+                s = ge;
+            }
+        }
+    }
+    if (S.prof && (threadIdx.x & 31) == 0) {
+        unsigned long long* o = g.prof + (size_t)blockIdx.x * 8;
+        o[0] = clk() - t_begin; o[1] = S.t_act; o[2] = S.t_stage;
+    }
+}
+
+template <int PI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PI == 0 ? kThreads : kThreads - kEncThreads, 1)
+mlp_tc_pair_kernel(const ChainArgs g, const __grid_constant__ PairMaps maps) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* act_all = smem;
+    uint8_t* ring = smem + kRingOff;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ring + kSlots * kSlotBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)tc::cluster_ctarank();
+    if (threadIdx.x == 0 && (tc::smem_u32(smem) & 1023u) != 0) {
+        printf("ddnerf mlp_tc: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    if (warp == 9 && lane == 0) {
+        for (int s = 0; s < kSlots; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
+        for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 2); }
+        for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->enc_ready[t], 1); tc::mbar_init(&ctl->enc_free[t], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 8 && lane == 0) {
+        for (int m = 0; m < kPairMaps; ++m) tc::prefetch_tensormap(&maps.m[m]);
+    }
+    tc::cluster_sync();                              // the barriers of both CTAs exist before anyone signals them
+    if (warp == 8) tc::tmem_alloc2(&ctl->tmem_base, 512);
+    tc::tc_fence_before_sync();
+    tc::cluster_sync();
+    tc::tc_fence_after_sync();
+
+    const int n_units = (g.n_items + 1) >> 1;
+    const Topo tp{(int)(blockIdx.x >> 1), (int)(gridDim.x >> 1), n_units, 1, rank, g.n_items * 2,
+                  tc::mapa_u32(tc::smem_u32(&ctl->act_ready[0]), 0)};
+    if (warp < 8) {
+        if (PI == 0) epilogue_fwd(g, tp, ctl, act_all, warp, lane);
+        else epilogue_bwd(g, tp, ctl, act_all, warp, lane);
+    } else if (warp == 8) {
+        producer_pair<PI>(g, tp, ctl, ring, maps);
+    } else if (warp == 9) {
+        if (rank == 0) mma_pair<PI>(g, tp, ctl, tc::smem_u32(smem));
+    } else {
+        if (PI == 0 && g.enc_mode) encoder_role(g, tp, ctl, (int)threadIdx.x - 320);
+    }
+
+    tc::tc_fence_before_sync();
+    tc::cluster_sync();                              // the leader's MMAs read the peer's shared memory and write its TMEM
+    if (warp == 8) tc::tmem_dealloc2(ctl->tmem_base, 512);
 }
 
 // ---- weight packing: fp32 nn.Linear parameters -> bf16 stage images in program order -----------
@@ -732,15 +1069,27 @@ __global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict
 // block of item n - 2 land in the ring, the producer starts item n's loads when the image is complete.  The image is
 // written with ordinary stores and read back by the TMA engine (bulk copies): fence.proxy.async orders the two proxies,
 // the named barrier + mbarrier arrive / wait carry the release / acquire.
-__device__ void encoder_role(const ChainArgs& g, SmemCtl* ctl, int tid) {
+__device__ void encoder_role(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, int tid) {
     uint32_t n = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++n) {
+    for (int unit = tp.first; unit < tp.n_units; unit += tp.step, ++n) {
         const uint32_t par = n & 1u;
         if (n >= 2) tc::mbar_wait(&ctl->enc_free[par], ((n >> 1) - 1u) & 1u);
-        uint8_t* ib = const_cast<uint8_t*>(g.enc) + (g.enc_mode == 2 ? (size_t)(blockIdx.x * 2u + par) : (size_t)item) * kEncItemBytes;
+        uint8_t* scratch = const_cast<uint8_t*>(g.enc) + (size_t)(blockIdx.x * 2u + par) * kEncItemBytes;
 #pragma unroll 1
-        for (int rr = tid; rr < kItemRows; rr += kEncThreads)
-            encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, (int64_t)item * kItemRows + rr, ib, rr >> 7, rr & 127);
+        for (int rr = tid; rr < kItemRows; rr += kEncThreads) {
+            const int T = rr >> 7, r = rr & 127;
+            if (!tp.pair) {              // this CTA's 256-row item: tile T of the item image
+                uint8_t* ib = g.enc_mode == 2 ? scratch : const_cast<uint8_t*>(g.enc) + (size_t)unit * kEncItemBytes;
+                encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, (int64_t)unit * kItemRows + rr, ib, T, r);
+            } else {                     // rows [128 rank, +128) of super-tile T = tile `rank` of 256-row item 2 unit + T
+                const int item = 2 * unit + T;
+                const int64_t row = ((int64_t)item * 2 + tp.rank) * 128 + r;
+                if (g.enc_mode == 2) encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, row, scratch, T, r);
+                else if (item < g.n_items)
+                    encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, row, const_cast<uint8_t*>(g.enc) + (size_t)item * kEncItemBytes,
+                                     tp.rank, r);
+            }
+        }
         tc::fence_proxy_async_all();
         named_bar(2, kEncThreads);
         if (tid == 0) tc::mbar_arrive(&ctl->enc_ready[par]);
@@ -882,8 +1231,159 @@ struct Builder {
     }
 };
 
+
+// ---- CTA-pair programs: the same packed weight image, walked per super-tile ------------------------------------
+struct PairBuilder {
+    PProgram P{};
+    std::vector<uint32_t> woff;      // byte offsets of the weight stages in the packed image, in load order
+    size_t wi = 0;
+    bool ok = true;
+    char why[160] = "";
+
+    uint32_t next_w(uint32_t bytes, const std::vector<uint32_t>& sizes) {
+        if (wi >= woff.size() || sizes[wi] != bytes) { ok = false; snprintf(why, sizeof(why), "pair program: weight stage %zu mismatch", wi); return 0; }
+        return woff[wi++];
+    }
+    PStage& add(uint8_t kind, int n_chunks, int last_nk16, int flags, int a_chunk0, int n, uint16_t b_stride) {
+        PStage& S = P.st[P.n_stages++];
+        S = PStage{};
+        S.kind = kind; S.n_chunks = (uint8_t)n_chunks; S.last_nk16 = (uint8_t)last_nk16; S.flags = (uint8_t)flags;
+        S.a_chunk0 = (uint8_t)a_chunk0; S.b_stride = b_stride; S.idesc = tc::idesc_bf16(256, n, 0, 0);
+        return S;
+    }
+    static void copy(PStage& S, uint8_t map, uint32_t idx, uint8_t mul, uint16_t dst_off, uint32_t bytes_per_cta) {
+        PCopy& C = S.c[S.n_copies++];
+        C = PCopy{idx, mul, map, dst_off};
+        S.tx_bytes += 2 * bytes_per_cta;
+    }
+};
+
+// `single` = the finished single-CTA builder of the same program (source of the weight offsets and the epilogue list)
+bool build_pair(const Builder& single, bool fwd, PProgram& out, uint32_t (&bases)[3], char* why, size_t n) {
+    PairBuilder b;
+    std::vector<uint32_t> sizes;
+    for (int i = 0; i < single.P.n_loads; ++i)
+        if (single.P.loads[i].kind == LOAD_W && single.P.loads[i].bytes > 16) {
+            b.woff.push_back(single.wbase + single.P.loads[i].off);
+            sizes.push_back(single.P.loads[i].bytes);
+        }
+    // The N = 256 chunks of a program are contiguous from `w128_base` (16 KB each), the view-branch chunks from `w72_base`
+    // (9216 B each); a copy with the traversal stride of the maps brings this CTA's halves of chunks c and c + 1; one-chunk
+    // stages use the single-half maps.
+    uint32_t w128_base = 0xFFFFFFFFu, w72_base = 0xFFFFFFFFu, w8_base = 0;
+    for (size_t i = 0; i < b.woff.size(); ++i) {
+        if (sizes[i] == 16384 && w128_base == 0xFFFFFFFFu) w128_base = b.woff[i];
+        if (sizes[i] == 9216 && w72_base == 0xFFFFFFFFu) w72_base = b.woff[i];
+        if (sizes[i] == 4096) w8_base = b.woff[i];
+    }
+    // Default: every stage per super-tile, the super-tiles a whole layer apart.  DDNERF_TC_PAIR_SHARE=1 selects the shared-stage
+    // schedule (half a layer apart, half the L2 -> SM traffic): measured 10 % slower at inference (the epilogue no longer fits
+    // behind the other super-tile's MMAs), equal in training.
+    const char* share_env = getenv("DDNERF_TC_PAIR_SHARE");
+    const int share = (share_env && atoi(share_env) == 1) ? PF_SHARED : 0;
+    auto w128x2 = [&](PStage& S, int nc, uint16_t dst) {          // nc chunks (1 or 2) starting at the next weight stage
+        const uint32_t off = b.next_w(16384, sizes);
+        if (nc > 1) b.next_w(16384, sizes);
+        if ((off - w128_base) % 16384) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program: N = 256 chunks are not contiguous"); }
+        PairBuilder::copy(S, nc > 1 ? PM_W128 : PM_W128S, 2 * ((off - w128_base) / 16384), 1, dst, nc > 1 ? 16384 : 8192);
+    };
+    auto w72x2 = [&](PStage& S, int nc, uint16_t dst) {
+        const uint32_t off = b.next_w(9216, sizes);
+        if (nc > 1) b.next_w(9216, sizes);
+        if ((off - w72_base) % 9216) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program: view-branch chunks are not contiguous"); }
+        PairBuilder::copy(S, nc > 1 ? PM_W72 : PM_W72S, 2 * ((off - w72_base) / 9216), 1, dst, nc > 1 ? 9216 : 4608);
+    };
+    // encoded 8 KB blocks of tile `tsel` inside a 64 KB item image: b0, b1 = blocks 2 tsel, 2 tsel + 1; b2 = 4 + tsel; view directions 6 + tsel
+    auto enc = [&](PStage& S, int blk) {
+        const uint32_t idx = blk < 2 ? (uint32_t)blk : (blk == 2 ? 4u : 6u);
+        PairBuilder::copy(S, PM_ENC, idx, blk < 2 ? 2 : 1, 0, 8192);
+    };
+    auto act_layer = [&](int n_chunks_total, int nmma, bool first, bool commit, int wait_flag, bool dir) {      // K = 32 n_chunks_total over the act buffer
+        for (int c = 0; c < n_chunks_total; c += 2) {
+            const int nc = std::min(2, n_chunks_total - c);
+            int flags = 0;
+            if (c == 0 && first) flags |= PF_FIRST | wait_flag;
+            if (c + 2 >= n_chunks_total && commit) flags |= PF_COMMIT_ACC;
+            PStage& S = b.add(PS_ACT, nc, 2, flags | share, c, nmma, dir ? 4608 : 8192);
+            if (dir) w72x2(S, nc, 0); else w128x2(S, nc, 0);
+        }
+    };
+    auto xyz_part = [&](bool first, int wait_flag) {       // K = 96 over the encoded xyz blocks, commits the accumulator
+        for (int c = 0; c < 3; ++c) {
+            int flags = 0;
+            if (c == 0 && first) flags |= PF_FIRST | wait_flag;
+            if (c == 2) flags |= PF_COMMIT_ACC;
+            PStage& S = b.add(PS_ENCW, 1, 2, flags, 0, 256, 8192);
+            enc(S, c);
+            w128x2(S, 1, 8192);
+        }
+    };
+    int e = 0;
+    auto begin_phase = [&] { b.P.phase_begin[e++] = (uint16_t)b.P.n_stages; };
+    if (fwd) {
+        begin_phase(); xyz_part(true, PF_WAIT_PREV);                                   // layers_xyz.0
+        for (int l = 1; l <= 8; ++l) {
+            begin_phase();
+            if (l == 5) { act_layer(8, 256, true, false, PF_WAIT_ACT, false); xyz_part(false, 0); }
+            else act_layer(8, 256, true, true, PF_WAIT_ACT, false);
+        }
+        begin_phase();                                                                  // view branch + density, N = 144
+        act_layer(8, 144, true, false, PF_WAIT_ACT, true);
+        {
+            PStage& S = b.add(PS_ENCW, 1, 2, PF_COMMIT_ACC | PF_ENC_DONE, 0, 144, 8192);
+            enc(S, 3);
+            w72x2(S, 1, 8192);
+        }
+        begin_phase();                                                                  // heads, N = 16: four [16 x 32] chunks, 8 rows per CTA
+        {
+            PStage& S = b.add(PS_HEADS, 4, 2, PF_FIRST | PF_WAIT_ACT | PF_COMMIT_ACC | share, 0, 16, 512);
+            b.next_w(4096, sizes);
+            PairBuilder::copy(S, PM_W8, 0, 1, 0, 2048);
+        }
+    } else {
+        begin_phase();                                                                  // EPI_BWD_IN: no MMAs
+        begin_phase();                                                                  // dZ_feat: K = 144 (4.5 chunks)
+        for (int c = 0; c < 5; c += 2) {
+            const int nc = std::min(2, 5 - c);
+            int flags = 0;
+            if (c == 0) flags |= PF_FIRST | PF_WAIT_ACT;
+            if (c == 4) flags |= PF_COMMIT_ACC;
+            PStage& S = b.add(PS_ACT, nc, c == 4 ? 1 : 2, flags | share, c, 256, 8192);
+            w128x2(S, nc, 0);
+        }
+        for (int p = 8; p >= 1; --p) { begin_phase(); act_layer(8, 256, true, true, PF_WAIT_ACT, false); }
+    }
+    b.P.phase_begin[e] = (uint16_t)b.P.n_stages;
+    b.P.n_phases = e;
+    for (int ph = 0; ph < e; ++ph) {        // plain layers take the issuer's unrolled path
+        const int s0 = b.P.phase_begin[ph], s1 = b.P.phase_begin[ph + 1];
+        bool fast = s1 - s0 == 4;
+        for (int s2 = s0; fast && s2 < s1; ++s2) {
+            const PStage& S = b.P.st[s2];
+            const int want = (s2 == s0 ? (PF_FIRST | PF_WAIT_ACT) : 0) | (s2 == s1 - 1 ? PF_COMMIT_ACC : 0) | share;
+            fast = S.kind == PS_ACT && S.n_chunks == 2 && S.last_nk16 == 2 && S.a_chunk0 == 2 * (s2 - s0) && S.b_stride == 8192 &&
+                   S.flags == want && S.idesc == tc::idesc_bf16(256, 256, 0, 0);
+        }
+        b.P.phase_fast[ph] = fast ? (share ? 2 : 1) : 0;
+        b.P.phase_idx0[ph] = b.P.st[s0].c[0].idx;
+        for (int s2 = s0; fast && s2 < s1; ++s2)
+            if (b.P.st[s2].n_copies != 1 || b.P.st[s2].c[0].map != PM_W128 || b.P.st[s2].c[0].idx != b.P.st[s0].c[0].idx + 4u * (s2 - s0) ||
+                b.P.st[s2].tx_bytes != 32768) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program: phase %d is not a plain layer", ph); }
+    }
+    if (b.ok && b.wi != b.woff.size()) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program: %zu of %zu weight stages used", b.wi, b.woff.size()); }
+    if (b.ok && e != single.P.n_epis) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program: %d phases for %d epilogues", e, single.P.n_epis); }
+    if (b.ok && b.P.n_stages > kMaxPStages) { b.ok = false; snprintf(b.why, sizeof(b.why), "pair program too large"); }
+    if (!b.ok) { snprintf(why, n, "%s", b.why); return false; }
+    out = b.P;
+    if (fwd) { bases[0] = w128_base; bases[1] = w72_base; bases[2] = w8_base; }
+    else { bases[0] = w128_base; bases[1] = bases[2] = w128_base; }
+    return true;
+}
+
 struct Programs {
     Builder fwd, bwd;
+    PProgram pfwd{}, pbwd{};
+    uint32_t pbase[2][3] = {};       // byte offsets of the pair maps' weight regions (N = 256, view branch, heads), per program
     PackTable pack{};
     bool ok = false;
     char why[160] = "";
@@ -960,6 +1460,8 @@ void build_into(Programs& S) {
     if (!S.bwd.finish(S.why, sizeof(S.why))) return;
     if (S.pack.n > kMaxPack) { snprintf(S.why, sizeof(S.why), "pack table too large"); return; }
     S.pack.total_bytes = S.fwd.woff + S.bwd.woff;
+    if (!build_pair(S.fwd, true, S.pfwd, S.pbase[0], S.why, sizeof(S.why))) return;
+    if (!build_pair(S.bwd, false, S.pbwd, S.pbase[1], S.why, sizeof(S.why))) return;
     S.ok = true;
 }
 
@@ -967,6 +1469,12 @@ Programs* build_programs() {            // host tables are built exactly once
     static Programs* S = [] { Programs* s = new Programs(); build_into(*s); return s; }();
     return S;
 }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+int g_pair_mode = -1;                   // -1: from DDNERF_TC_PAIR (default on); 0 single-CTA kernels; 1 CTA-pair kernels
 
 std::once_flag g_once;
 Programs* g_programs = nullptr;
@@ -981,6 +1489,14 @@ int ensure_programs() {
         if (cudaMemcpyToSymbol(c_pack, &g_programs->pack, sizeof(PackTable)) != cudaSuccess) g_upload_rc = 2;
         if (cudaFuncSetAttribute(mlp_tc_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
         if (cudaFuncSetAttribute(mlp_tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+        if (cudaMemcpyToSymbol(c_pprog, &g_programs->pfwd, sizeof(PProgram), 0) != cudaSuccess) g_upload_rc = 2;
+        if (cudaMemcpyToSymbol(c_pprog, &g_programs->pbwd, sizeof(PProgram), sizeof(PProgram)) != cudaSuccess) g_upload_rc = 2;
+        if (cudaFuncSetAttribute(mlp_tc_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+        if (cudaFuncSetAttribute(mlp_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) g_upload_rc = 3;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) g_upload_rc = 4;
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     });
     return g_upload_rc;
 }
@@ -1012,6 +1528,13 @@ using namespace ddnerf;
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_set_profile_buffer(void* dev_u64) {
     g_prof_buffer = static_cast<unsigned long long*>(dev_u64);
     return 0;
+}
+/* Kernel variant of the forward / dX chains: 1 = CTA pairs (cluster of 2, tcgen05 cta_group::2; the default), 0 = one CTA
+ * per work item, -1 = re-read DDNERF_TC_PAIR.  Returns the previous setting.  Results are bit-identical. */
+extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_set_pair_mode(int mode) {
+    const int prev = g_pair_mode;
+    g_pair_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+    return prev;
 }
 /* 0 when the static kernel programs (ring schedule, op tables) are consistent; host-only check */
 extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_program_check(void) {
@@ -1059,6 +1582,46 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_encode(const float* rays, const float
     return 0;
 }
 
+static bool pair_mode() {
+    if (g_pair_mode < 0) {
+        const char* e = getenv("DDNERF_TC_PAIR");
+        g_pair_mode = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_pair_mode == 1;
+}
+
+// A {512-byte row, rows_per_half, n_halves} view of the bytes at `base`, no swizzle (the images are pre-swizzled): a box is
+// `box_halves` halves traversed with element stride `estride` along the last dimension, landing contiguously in shared memory.
+static bool make_map(CUtensorMap* m, const void* base, uint32_t rows_per_half, uint64_t n_halves, uint32_t box_halves, uint32_t estride) {
+    const cuuint64_t dims[3] = {256, rows_per_half, n_halves}, strides[2] = {512, (cuuint64_t)rows_per_half * 512};
+    const cuuint32_t box[3] = {256, rows_per_half, box_halves}, estr[3] = {1, 1, estride};
+    return g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// wimg_base: start of the whole packed image (both programs); enc / enc_blocks: the encoded images the producer reads (or null)
+template <int PI>
+static int launch_pair(const char* who, const ChainArgs& g, const void* wimg_base, const void* enc, uint64_t enc_blocks, int max_ctas,
+                       void* stream) {
+    PairMaps maps;
+    const uint8_t* wb = static_cast<const uint8_t*>(wimg_base);
+    const uint32_t* base = g_programs->pbase[PI];
+    const uint64_t total = (uint64_t)g_programs->fwd.woff + g_programs->bwd.woff;
+    bool ok = make_map(&maps.m[PM_W128], wb + base[0], 16, (total - base[0]) / 8192, 3, 2) &&
+              make_map(&maps.m[PM_W72], wb + base[1], 9, (total - base[1]) / 4608, 3, 2) &&
+              make_map(&maps.m[PM_W8], wb + base[2], 1, (total - base[2]) / 512, 7, 2) &&
+              make_map(&maps.m[PM_W128S], wb + base[0], 16, (total - base[0]) / 8192, 1, 1) &&
+              make_map(&maps.m[PM_W72S], wb + base[1], 9, (total - base[1]) / 4608, 1, 1);
+    ok = ok && (enc ? make_map(&maps.m[PM_ENC], enc, 16, enc_blocks, 1, 1) : make_map(&maps.m[PM_ENC], wb, 16, total / 8192, 1, 1));
+    DDNERF_CHECK_ARG(ok, "%s: cuTensorMapEncodeTiled failed", who);
+    const int n_units = (g.n_items + 1) / 2;
+    int pairs = std::min(n_units, sm_count() / 2);
+    if (max_ctas > 0) pairs = std::max(1, std::min(pairs, max_ctas / 2));
+    mlp_tc_pair_kernel<PI><<<2 * pairs, PI == 0 ? kThreads : kThreads - kEncThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g, maps);
+    DDNERF_LAUNCHED(who, 1);
+    return 0;
+}
+
 static int launch_forward(const char* who, ChainArgs g, int64_t rows, void* stream) {
     const int64_t n_items = ddnerf_mlp_tc_items(rows);
     DDNERF_CHECK_ARG(n_items < (1 << 30), "%s: too many rows", who);
@@ -1066,6 +1629,10 @@ static int launch_forward(const char* who, ChainArgs g, int64_t rows, void* stre
     g.n_items = (int)n_items;
     if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
     g.prof = g_prof_buffer;
+    if (pair_mode()) {
+        const uint64_t enc_blocks = (g.enc_mode == 2 ? (uint64_t)sm_count() * 2 : (uint64_t)n_items) * (kEncItemBytes / 8192);
+        return launch_pair<0>(who, g, g.wimg, g.enc, enc_blocks, 0, stream);
+    }
     const int grid = (int)std::min<int64_t>(n_items, sm_count());
     mlp_tc_chain_kernel<0><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED(who, 1);
@@ -1147,9 +1714,10 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dx(const void* wimg, const f
     g.C = out_channels;
     if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
     g.prof = g_prof_buffer;
+    if (pair_mode()) return launch_pair<1>("mlp_tc_backward_dx", g, wimg, nullptr, 0, max_ctas, stream);
     int grid = (int)std::min<int64_t>(n_items, sm_count());
     if (max_ctas > 0) grid = std::min(grid, max_ctas);
-    mlp_tc_chain_kernel<1><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    mlp_tc_chain_kernel<1><<<grid, kThreads - kEncThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
     DDNERF_LAUNCHED("mlp_tc_backward_dx", 1);
     return 0;
 }

@@ -71,5 +71,51 @@ struct PackTable { int n; uint32_t total_bytes; PackEntry e[kMaxPack]; };
 
 enum : uint16_t { PK_FWD = 0, PK_FWD_DIR = 1, PK_FWD_HEADS = 2, PK_BWD = 3, PK_BWD_DIR = 4 };
 
+// ---- CTA-pair variant (cluster of 2, tcgen05 cta_group::2) ----------------------------------------
+// Work unit = 512 sample rows = two super-tiles of 256 rows; CTA `rank` of the pair holds rows [128 rank, 128 rank + 128)
+// of each super-tile (its act buffer T, its TMEM columns [256 T, 256 T + 256)), i.e. global 128-row tile
+// (2 unit + T) * 2 + rank.  One M = 256 MMA covers a super-tile; its B operand (a weight chunk [N x 32 k]) is split by
+// rows between the two CTAs, so a 16 KB ring slot holds TWO K = 32 chunks (K = 64) and the 6-slot ring 1.5 layers.
+// The two super-tiles run a whole layer apart: every stage is fetched once per super-tile (same L2 -> SM bytes per row as the
+// single-CTA kernel) and released right behind its MMAs, and a super-tile's epilogue has the other one's whole layer of MMAs
+// to hide in.  With PF_SHARED on the weight-only stages the same code runs them half a layer (two stages) apart instead: T0
+// takes the stages as they land, T1 follows and releases them (half the L2 -> SM bytes; measured slower, see build_pair).
+// Stages arrive by tiled TMA (.cta_group::2) that signals the LEADER's barrier from both CTAs.
+enum : uint8_t { PS_ACT = 0,      // 1-2 weight chunks; A = act-buffer K = 32 chunks a_chunk0, a_chunk0 + 1
+                 PS_ENCW = 1,     // [encoded block (A operand) | weight chunk] in one slot
+                 PS_HEADS = 2 };  // four [16 x 32] chunks of the colour / (mu, sigma) heads; A = act chunks 0..3
+enum : uint8_t { PF_FIRST = 1, PF_COMMIT_ACC = 2, PF_WAIT_ACT = 4, PF_WAIT_PREV = 8, PF_ENC_DONE = 16,
+                 PF_SHARED = 32 };    // the stage serves BOTH super-tiles (weights only): loaded once, T0 then T1 consume it, T1 releases
+// Tensor maps: 3-D views {512-byte row, rows of one chunk HALF, half index}.  The halves of a weight chunk lie one after the
+// other (rank 0's N/2 rows, then rank 1's), so half 2 c + rank belongs to chunk c; a box of 3 halves traversed with element
+// stride 2 delivers this CTA's halves of TWO consecutive chunks as one copy (contiguous in the slot).  PM_W128: 8 KB halves
+// of the N = 256 chunks of the launched program; PM_W72: 4.5 KB halves of the view-branch chunks (N = 144); PM_W8: 512-byte
+// halves of the four head chunks (box 7 -> four halves); PM_ENC: the 8 KB encoded blocks, one per copy.
+enum : uint8_t { PM_W128 = 0, PM_W72 = 1, PM_W8 = 2, PM_ENC = 3,
+                 PM_W128S = 4, PM_W72S = 5 };      // single halves (one-chunk stages)
+constexpr int kPairMaps = 6;
+struct PCopy {
+    uint32_t idx;        // half / block index in the map; weights: + rank; encoded blocks: + tsel * mul + 8 * image
+    uint8_t mul, map;
+    uint16_t dst_off;    // byte offset inside the ring slot
+};
+struct __align__(16) PStage {
+    uint8_t kind, n_chunks, last_nk16, flags;
+    uint8_t a_chunk0, n_copies;
+    uint16_t b_stride;   // bytes between the B blocks of consecutive chunks inside the slot
+    uint32_t idesc;
+    uint32_t tx_bytes;   // bytes landing in BOTH CTAs
+    PCopy c[2];
+};
+constexpr int kMaxPStages = 48;
+struct PProgram {
+    int n_stages, n_phases;
+    uint16_t phase_begin[kMaxEpis + 1];      // stages [phase_begin[e], phase_begin[e+1]) run before epilogue e
+    uint8_t phase_fast[kMaxEpis + 3];        // a plain K = 256, N = 256 layer over the act buffer (four two-chunk stages) takes an unrolled
+                                             // issue path: 1 = per super-tile, 2 = shared stages
+    uint32_t phase_idx0[kMaxEpis + 1];       // fast phases: PM_W128 index of the first stage's copy (stage st: + 4 st, + rank)
+    PStage st[kMaxPStages];
+};
+
 }  // namespace tcmlp
 }  // namespace ddnerf

@@ -169,6 +169,57 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
         ::"r"(bar), "r"(rank)
         : "memory");
 }
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier given by its shared::cluster address (any CTA of the cluster).  Default semantics (release at CTA
+// scope), as CUTLASS' ClusterBarrier::arrive: the data handed over is this CTA's OWN shared memory, read by the pair's
+// tensor-core operation on this same SM, and a release at cluster scope costs > 1000 cycles per epilogue (measured).
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals come from both CTAs of a pair)
+__device__ __forceinline__ void mbar_wait_cluster_u32(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+#ifdef DDNERF_TC_WATCHDOG
+        if (++spins > (1u << 26)) { printf("ddnerf tc: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+#endif
+    }
+}
+// Tiled TMA load of a 2-D box into this CTA's shared memory, completing (in bytes) on an mbarrier that may live in
+// the PEER CTA of the pair (.cta_group::2): both CTAs of a pair signal the leader's "stage landed" barrier directly.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t mbar_cluster_addr,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_dst), "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t mbar_cluster_addr,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_dst), "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* holder, uint32_t ncols) {      // both CTAs, same warp index
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");

@@ -158,6 +158,10 @@ int ddnerf_mlp_tc_forward_rays(const void* wimg, const float* bias_pack, const f
                                float* out, void* enc_img, void* enc_scratch, void* act_save,
                                void* mask_save, void* stream);
 int ddnerf_mlp_tc_program_check(void);
+/* Kernel variant of the forward and dX chains (base_architectures.py:89-126, same arithmetic, bit-identical results):
+ * 1 = CTA pairs (cluster of 2, tcgen05 cta_group::2 with the weight chunks split across the pair; default),
+ * 0 = one CTA per 256-row work item, -1 = re-read the DDNERF_TC_PAIR environment variable.  Returns the previous setting. */
+int ddnerf_mlp_tc_set_pair_mode(int mode);
 /* Diagnostic hook of the dW kernel: a device buffer of >= 4 * 480 uint64 receives, per work item of the next
  * launches, {layer-op, tiles, cycles until its last MMA completed, cycles of its flush}; NULL switches it off. */
 int ddnerf_mlp_tc_dw_set_profile_buffer(void* dev_u64);

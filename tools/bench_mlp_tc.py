@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--save", action="store_true", help="training forward (store activations + masks)")
     ap.add_argument("--prof", action="store_true", help="print the chain kernels' per-role cycle counters")
+    ap.add_argument("--pair", type=int, default=-1, help="1: CTA-pair chain kernels, 0: single-CTA kernels, -1: library default")
     args = ap.parse_args()
     from oracle import ddnerf_oracle as orc
     from ddnerf_b200 import _lib, mlp_tc
@@ -28,6 +29,7 @@ def main():
     from ddnerf_b200.ops import _p, _stream
     from ddnerf_b200.rays import synth_rays
     lib = _lib.load()
+    lib.ddnerf_mlp_tc_set_pair_mode(args.pair)
     N, S = args.rays, args.samples
     ro, rd, rad, near, far = synth_rays("blender", N, seed=1)
     rays = orc.pack_rays(ro, rd, rad, near, far).cuda()
@@ -71,7 +73,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     flops = 2.0 * 610304 * rows
-    res.update(rows=rows, fwd_ms=ms, fwd_tflops=flops / ms / 1e9, save=bool(args.save))
+    res.update(pair=args.pair, rows=rows, fwd_ms=ms, fwd_tflops=flops / ms / 1e9, save=bool(args.save))
 
     # the model path: ONE launch, the chain kernel's own encoder warps (no standalone encode)
     scratch = torch.empty(lib.ddnerf_mlp_tc_enc_scratch_bytes(), device="cuda", dtype=torch.uint8)
@@ -130,7 +132,11 @@ def main():
             buf.zero_()
             fn()
             torch.cuda.synchronize()
-            b = buf.view(148, 8).double()[0::2]          # leader CTAs of the pairs
+            if args.pair != 0:
+                pb_ = buf.view(148, 8).double()[1::2]
+                pt, pe, pn = [pb_[:, i].mean().item() for i in range(3)]
+                print(f"{name}: peer producer total {pt:.0f} cyc | waiting for free slots {100 * pe / max(pt, 1):.1f}% | for the encoder {100 * pn / max(pt, 1):.1f}%")
+            b = buf.view(148, 8).double()[0::2] if args.pair != 0 else buf.view(148, 8).double()
             tot, t_act, t_stage, e_wait, e_busy, n, e_pre, e_work = [b[:, i].mean().item() for i in range(8)]
             if os.environ.get("DDNERF_TC_PROF_ISSUER"):
                 print(f"{name}: issuer total {tot:.0f} | act waits {100*t_act/tot:.1f}% | T0 passes {100*t_stage/tot:.1f}% | waits for own stages {100*e_wait/tot:.1f}% | waits for the peer's {100*e_busy/tot:.1f}%")
