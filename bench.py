@@ -656,8 +656,9 @@ def main():
         if tag in by_tag:
             ms_step = sum(by_tag[tag]) / K_ev
             ach = work / (ms_step * 1e-3) / scale
-            breakdown.append({"kernel": {"fwd": "mlp_tc_chain_kernel<0> (forward + activation saves)",
-                                         "dx": "mlp_tc_chain_kernel<1> (dX chain)", "dw": "mlp_tc_dw_kernel (dW, db)"}[tag],
+            chain = "mlp_tc_pair_kernel" if os.environ.get("DDNERF_TC_PAIR", "1") != "0" else "mlp_tc_chain_kernel"
+            breakdown.append({"kernel": {"fwd": chain + "<0> (forward + activation saves)",
+                                         "dx": chain + "<1> (dX chain)", "dw": "mlp_tc_dw_kernel (dW, db)"}[tag],
                               "bound": bound, "launches_per_step": len(by_tag[tag]) // K_ev, "ms_per_step": ms_step,
                               "achieved": ach, "peak": peak_v, "unit": unit, "frac": ach / peak_v})
             if bound == "hbm":
@@ -699,7 +700,21 @@ def main():
     if rank == 0:
         emit(line)
     if world > 1:
+        # Teardown: the CUDA graphs that captured NCCL kernels must be gone before the communicator is destroyed (destroying
+        # it under live graphs can block for ever); a timer ends the process if the destroy still does not return.
+        import gc
+        import threading
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        del trainer, model
+        gc.collect()
+        torch.cuda.synchronize()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

@@ -62,6 +62,7 @@ struct ChainArgs {
     uint32_t* mask;           // [layers][n_tiles][128][8]: fwd writes (or null), bwd reads
     int64_t rows;
     int n_items, C;
+    int pslots;               // experiment knob (DDNERF_TC_PSLOTS): ring slots the pair kernels use (<= kSlots)
     int save_alias;           // experiment knob (DDNERF_TC_SAVE_ALIAS): saves go to tile % save_alias (L2-resident)
     unsigned long long* prof; // optional [grid][8] cycle counters (ddnerf_mlp_tc_set_profile_buffer), else null
 };
@@ -652,7 +653,7 @@ __device__ void producer_pair(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, 
                             tc::tma_load_3d_pair(ring_u32 + slot * kSlotBytes, &maps.m[PM_W128], 0, 0, (int)(idx0 + 4u * st), full_leader + slot * 8u, pol_w);
                         }
                         __syncwarp();
-                        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+                        if (++slot == (uint32_t)g.pslots) { slot = 0; phase ^= 1; }
                     }
                 }
                 continue;
@@ -693,7 +694,7 @@ __device__ void producer_pair(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, 
                             }
                         }
                         __syncwarp();
-                        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+                        if (++slot == (uint32_t)g.pslots) { slot = 0; phase ^= 1; }
                     }
                 }
                 s = ge;
@@ -727,8 +728,9 @@ struct PairIssuer {
         tc::mbar_wait_u32(full0 + slot * 8u, phase);
         if (prof) t_stage += clk() - t0;
     }
+    uint32_t nslots;
     __device__ __forceinline__ void advance() {
-        if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+        if (++slot == nslots) { slot = 0; phase ^= 1u; }
     }
 };
 
@@ -743,6 +745,7 @@ __device__ void mma_pair(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, uint3
     S.acc0 = tc::smem_u32(&ctl->acc_full[0]);
     S.act0 = tc::smem_u32(&ctl->act_ready[0]);
     S.slot = S.phase = S.act_phase = 0;
+    S.nslots = (uint32_t)g.pslots;
     S.t_act = S.t_stage = 0;
     S.prof = g.prof != nullptr;
     const uint32_t encf0 = tc::smem_u32(&ctl->enc_free[0]);
@@ -1601,8 +1604,11 @@ static bool make_map(CUtensorMap* m, const void* base, uint32_t rows_per_half, u
 
 // wimg_base: start of the whole packed image (both programs); enc / enc_blocks: the encoded images the producer reads (or null)
 template <int PI>
-static int launch_pair(const char* who, const ChainArgs& g, const void* wimg_base, const void* enc, uint64_t enc_blocks, int max_ctas,
+static int launch_pair(const char* who, const ChainArgs& g_in, const void* wimg_base, const void* enc, uint64_t enc_blocks, int max_ctas,
                        void* stream) {
+    ChainArgs g = g_in;
+    g.pslots = kSlots;
+    if (const char* e = getenv("DDNERF_TC_PSLOTS")) g.pslots = std::max(2, std::min(kSlots, atoi(e)));
     PairMaps maps;
     const uint8_t* wb = static_cast<const uint8_t*>(wimg_base);
     const uint32_t* base = g_programs->pbase[PI];

@@ -649,3 +649,42 @@ def test_bf16_cfg3_ff_validation_slab_vs_oracle():
     e_cd = _report("corrected disp", out[0]["corrected_disp_map"].reshape(-1).cpu(), ref[0]["corrected_disp_map"], 5e-3)
     rel = (e_cd / ref[0]["corrected_disp_map"].abs().clamp(min=1e-6)).max().item()
     assert rel < 5e-3
+
+
+@pytest.mark.parametrize("N,S,depth_head", [(3, 128, False), (5, 256, True), (7, 128, False), (1, 16, True), (1024, 32, True),
+                                            (2048, 128, False)])
+def test_pair_kernels_bit_identical_to_single_cta(N, S, depth_head):
+    """The CTA-pair chain kernels (cluster of 2, tcgen05 cta_group::2: M = 256 MMAs, weight chunks split across the
+    pair, tiled TMA signalling the leader's barrier; the default) against the single-CTA kernels on the same inputs:
+    forward outputs (training, inference with the in-kernel encoder, image-fed), saved activations, ReLU masks,
+    encoded images and the dX chain's dZ images must be BIT-identical -- same K order, same epilogues.  Row counts
+    that leave the last 512-row unit of a pair half or three quarters empty are included."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import check_pair
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200 import _lib, mlp_tc
+    from ddnerf_b200.models import base_architectures as BA
+    from ddnerf_b200.rays import synth_rays
+    lib = _lib.load()
+    torch.manual_seed(N)
+    ro, rd, rad, near, far = synth_rays("blender", N, seed=1)
+    rays = orc.pack_rays(ro, rd, rad, near, far).cuda()
+    t_vals = orc.sample_first_cycle(rays[:, 7:8].cpu(), rays[:, 8:9].cpu(), S).cuda()
+    net = (BA.DepthMipNeRFModel if depth_head else BA.MipNeRFModel)(
+        hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True)
+    net.to("cuda")
+    C = 6 if depth_head else 4
+    st = mlp_tc._state(net)
+    st.refresh()
+    gout = torch.randn(N * S, C, device="cuda")
+    prev = lib.ddnerf_mlp_tc_set_pair_mode(0)
+    try:
+        a = check_pair.run(lib, 0, C, rays, t_vals, st, gout)
+        b = check_pair.run(lib, 1, C, rays, t_vals, st, gout)
+    finally:
+        lib.ddnerf_mlp_tc_set_pair_mode(prev)
+    assert torch.isfinite(b["out"]).all()
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"{k} differs between the single-CTA and the CTA-pair kernels"
