@@ -50,7 +50,7 @@ def main():
         f.write("# SASS opcode histogram of `ddnerf_b200/libddnerf_b200.so` (sm_100a)\n\n")
         f.write("`python tools/sass_opcodes.py` = `cuobjdump -sass` of the shipped library, instructions counted per kernel.\n"
                 "UTCHMMA = `tcgen05.mma`, UTCBAR = `tcgen05.commit`, LDTM = `tcgen05.ld`, UBLKCP = `cp.async.bulk` (TMA engine, "
-                "plain byte ranges of pre-swizzled operand images; no tensor map, hence no UTMALDG), SYNCS = mbarrier, "
+                "plain byte ranges of pre-swizzled operand images; the single-CTA kernels and the dW kernel need no tensor map; the CTA-pair chain kernels fetch their ring stages with tiled TMA = UTMALDG.3D.2CTA so that both CTAs signal the leader's barrier), SYNCS = mbarrier, "
                 "MUFU = SFU, RED/ATOM = global reductions.\n\n")
         f.write("| kernel | instr | " + " | ".join(WATCH) + " |\n|---|---:|" + "---:|" * len(WATCH) + "\n")
         for short, c in rows:
