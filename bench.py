@@ -669,10 +669,11 @@ def main():
     if breakdown:
         line["roofline"]["breakdown"] = breakdown
         # DRAM bytes per step of the three MLP kernels from the committed ncu --set full captures
-        # (profiles/r01b_ncu_mlp_tc_{fwd,dx,dw}.md: read + write per launch at 524,288 rows), scaled by rows
-        per_row = ((0.244e9 + 2.650e9) + (0.175e9 + 2.558e9) + (5.810e9 + 0.009e9)) / 524288.0
+        # (profiles/r02j_ncu_mlp_tc_{pair_fwd_rays,pair_dx,dw}.md: read + write per launch at 524,288 rows), scaled by rows
+        per_row = ((0.1007e9 + 2.7837e9) + (0.1606e9 + 2.5575e9) + (5.8592e9 + 0.0064e9)) / 524288.0
         line["roofline"]["traffic"] = per_row * rows_step if args.mlp_mode == "bf16" else None
-        line["roofline"]["traffic_note"] = "dram__bytes_read+write of fwd/dx/dw from profiles/r01b_ncu_mlp_tc_*.md, per step"
+        line["roofline"]["traffic_note"] = ("dram__bytes_read+write of the forward (ray-fed, with saves), dX chain and dW kernels from "
+                                            "profiles/r02j_ncu_mlp_tc_{pair_fwd_rays,pair_dx,dw}.md, per step")
     if not args.no_cfg4 and args.workload != "cfg4":
         line["train_cfg4"] = run_train_block(args, "cfg4", dev, world, rank, dist, K, W)
     if not args.no_render:

@@ -13,6 +13,7 @@
 // colour / (mu, sigma) heads (5 weighted column sums of the view-branch activations).
 // HBM-bound by design: 128 KB of tile images per 16.8 MFLOP.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #define DDNERF_TC_WATCHDOG 1
@@ -82,6 +83,7 @@ struct DwArgs {
     int n_tiles, C;
     int n_work;
     unsigned long long* prof;   // diagnostic: per work item {op, tiles, cycles to the last MMA, cycles of the flush}
+    uint32_t dz_alias;          // experiment knob (DDNERF_TC_DW_DZ_ALIAS): dZ images are read from tile % dz_alias (L2-resident)
 };
 struct DwWork { WorkItem w[kMaxWork]; uint16_t first[kMaxCtas + 1]; };   // CTA i: items first[i] .. first[i+1]-1
 
@@ -108,7 +110,7 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 __device__ void dw_producer(const DwArgs& g, const DwOp& op, const WorkItem wk, DwCtl* ctl, uint8_t* ring, uint32_t& s, uint32_t& phase) {
     const size_t layer_pitch = (size_t)g.n_tiles * kActBytes;
     for (uint32_t t = wk.t0; t < wk.t1; ++t) {
-        const uint8_t* a_src = op.a_layer >= 0 ? g.dz + op.a_layer * layer_pitch + (size_t)t * kActBytes : nullptr;
+        const uint8_t* a_src = op.a_layer >= 0 ? g.dz + op.a_layer * layer_pitch + (size_t)(g.dz_alias ? t % g.dz_alias : t) * kActBytes : nullptr;
         const uint8_t* b_src = op.b_layer >= 0 ? g.act + op.b_layer * layer_pitch + (size_t)t * kActBytes : nullptr;
         const uint8_t* e_src = g.enc + (size_t)(t >> 1) * kEncItemBytes;
         const uint32_t T = t & 1u;
@@ -397,6 +399,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_backward_dw(const void* act_save, con
     g.C = out_channels;
     g.n_work = n_work;
     g.prof = g_dw_prof;
+    if (const char* e = getenv("DDNERF_TC_DW_DZ_ALIAS")) g.dz_alias = (uint32_t)atoi(e);
     mlp_tc_dw_kernel<<<n_work, kDwThreads, kDwSmemBytes, static_cast<cudaStream_t>(stream)>>>(g, work);
     DDNERF_LAUNCHED("mlp_tc_backward_dw", 1);
     return 0;
