@@ -38,6 +38,9 @@ def run(lib, mode, net_C, rays, t_vals, st, gout):
 
 
 def main():
+    import hashlib
+    import json
+    digests = {}
     from oracle import ddnerf_oracle as orc
     from ddnerf_b200 import _lib, mlp_tc
     from ddnerf_b200.models import base_architectures as BA
@@ -69,7 +72,11 @@ def main():
                     print(f"  N={N} S={S} C={C} {k}: {nd} of {x.numel()} bytes differ, first at {first}")
                 else:
                     print(f"  N={N} S={S} C={C} {k}: max abs diff {(x - y).abs().max().item():.3e}, nan {torch.isnan(y).sum().item()}")
+        for k in b:        # digests of the written parts (uninitialised bytes of the image buffers are zero: the buffers start zeroed)
+            digests[f"{N}x{S}x{C}:{k}"] = hashlib.sha1(b[k].cpu().numpy().tobytes()).hexdigest()
         print(f"N={N} S={S} C={C}: " + ("identical" if all(torch.equal(a[k], b[k]) for k in a) else "DIFFERENT"), flush=True)
+    if len(sys.argv) > 1:          # digests for comparing two processes (e.g. DDNERF_TC_REG_SAVES=0 against the default)
+        json.dump(digests, open(sys.argv[1], "w"), indent=0)
     print("check_pair:", "OK" if bad == 0 else f"{bad} mismatches")
     sys.exit(0 if bad == 0 else 1)
 
