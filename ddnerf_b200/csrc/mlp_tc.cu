@@ -62,6 +62,7 @@ struct ChainArgs {
     uint32_t* mask;           // [layers][n_tiles][128][8]: fwd writes (or null), bwd reads
     int64_t rows;
     int n_items, C;
+    int enc_yield;            // the in-kernel encoder yields to the epilogue warps (DDNERF_TC_ENC_YIELD, default 1)
     int pslots;               // experiment knob (DDNERF_TC_PSLOTS): ring slots the pair kernels use (<= kSlots)
     int save_alias;           // experiment knob (DDNERF_TC_SAVE_ALIAS): saves go to tile % save_alias (L2-resident)
     unsigned long long* prof; // optional [grid][8] cycle counters (ddnerf_mlp_tc_set_profile_buffer), else null
@@ -87,7 +88,9 @@ constexpr uint32_t kHi64 = (uint32_t)(tc::smem_desc(0, 0, 512, tc::LAYOUT_SW64) 
 struct __align__(16) SmemCtl {
     uint64_t full[kSlots], empty[kSlots], acc_full[2], act_ready[2];
     uint64_t enc_ready[2], enc_free[2];  // encoder -> producer: image of item parity p written; MMA warp -> encoder: consumed
-    uint32_t tmem_base, pad[3];
+    uint32_t tmem_base;
+    uint32_t epi_busy;                   // forward: the epilogue warps are converting an accumulator (the encoder warps hold back meanwhile)
+    uint32_t pad[2];
     float bias[2][256];
 };
 constexpr int kSmemBytes = 2 * kActBytes + kSlots * kSlotBytes + (int)sizeof(SmemCtl);
@@ -172,6 +175,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, u
                 tc::mbar_wait(&ctl->acc_full[T], (acc_phase >> T) & 1u);
                 acc_phase ^= 1u << T;
                 tc::tc_fence_after_sync();
+                if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&ctl->epi_busy) = 1u;
                 const unsigned long long tw1 = g.prof ? clk() : 0;
                 if (g.save) {            // this tile's previous bulk store must have finished reading the act buffer
                     if (tid == 0 && stores >= 2) tc::bulk_wait_read<1>();
@@ -252,6 +256,7 @@ __device__ void epilogue_fwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, u
                 named_bar(1, kEpiThreads);
                 if (tid == 0) {
                     signal_act_ready(tp, ctl, T);
+                    *reinterpret_cast<volatile uint32_t*>(&ctl->epi_busy) = 0u;
                     if (g.prof) { t_wait += tw1 - tw0; t_busy += clk() - tw1; ++n_epi; t_pre += tw2 - tw1; t_work += tw3 - tw2; }
                     if (g.save && E.save_layer >= 0) {
                         const int tile_s = g.save_alias ? tile_g % g.save_alias : tile_g;
@@ -586,6 +591,7 @@ __global__ void __launch_bounds__(PI == 0 ? kThreads : kThreads - kEncThreads, 1
         for (int t = 0; t < 2; ++t) { tc::mbar_init(&ctl->enc_ready[t], 1); tc::mbar_init(&ctl->enc_free[t], 1); }
         tc::fence_barrier_init();
     }
+    if (threadIdx.x == 0) ctl->epi_busy = 0u;
     if (warp == 8) tc::tmem_alloc(&ctl->tmem_base, 512);
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -894,6 +900,7 @@ mlp_tc_pair_kernel(const ChainArgs g, const __grid_constant__ PairMaps maps) {
     }
     if (warp == 8 && lane == 0) {
         for (int m = 0; m < kPairMaps; ++m) tc::prefetch_tensormap(&maps.m[m]);
+        ctl->epi_busy = 0u;
     }
     tc::cluster_sync();                              // the barriers of both CTAs exist before anyone signals them
     if (warp == 8) tc::tmem_alloc2(&ctl->tmem_base, 512);
@@ -997,8 +1004,11 @@ __device__ __forceinline__ float safe_arg_fast(float x) {          // math_utils
 }
 
 // one sample row of the operand image: `row` = global sample row, (T, r) = its tile and row inside the 256-row item at `ib`
+// `busy` (encoder warps of the chain kernel): shared flag the epilogue warps raise while they work; the encoder yields the issue
+// slots it shares with them between octaves (bounded wait), i.e. it runs in the gaps in which they wait for the tensor pipe
 __device__ __forceinline__ void encode_row_image(const float* __restrict__ rays, const float* __restrict__ t_vals, int64_t N, int S,
-                                                 int ray_shape, int64_t row, uint8_t* __restrict__ ib, int T, int r) {
+                                                 int ray_shape, int64_t row, uint8_t* __restrict__ ib, int T, int r,
+                                                 const volatile uint32_t* busy = nullptr) {
     uint32_t w[48];                       // 96 bf16: feature f = h*48 + l*3 + a in word f/2
     uint32_t dw[16];                      // 32 bf16 of the direction block
 #pragma unroll
@@ -1016,6 +1026,9 @@ __device__ __forceinline__ void encode_row_image(const float* __restrict__ rays,
 #pragma unroll
         for (int l = 0; l < 16; ++l) {
             const float scale = (float)(1 << l), sc2 = scale * scale;
+            if (busy && (l & 1) == 0) {
+                for (int spins = 0; *busy && spins < 48; ++spins) __nanosleep(64);
+            }
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const float y = m[a] * scale;
@@ -1074,6 +1087,7 @@ __global__ void __launch_bounds__(128) encode_img_kernel(const float* __restrict
 // the named barrier + mbarrier arrive / wait carry the release / acquire.
 __device__ void encoder_role(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, int tid) {
     uint32_t n = 0;
+    const volatile uint32_t* busy = g.enc_yield ? &ctl->epi_busy : nullptr;
     for (int unit = tp.first; unit < tp.n_units; unit += tp.step, ++n) {
         const uint32_t par = n & 1u;
         if (n >= 2) tc::mbar_wait(&ctl->enc_free[par], ((n >> 1) - 1u) & 1u);
@@ -1083,14 +1097,14 @@ __device__ void encoder_role(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, i
             const int T = rr >> 7, r = rr & 127;
             if (!tp.pair) {              // this CTA's 256-row item: tile T of the item image
                 uint8_t* ib = g.enc_mode == 2 ? scratch : const_cast<uint8_t*>(g.enc) + (size_t)unit * kEncItemBytes;
-                encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, (int64_t)unit * kItemRows + rr, ib, T, r);
+                encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, (int64_t)unit * kItemRows + rr, ib, T, r, busy);
             } else {                     // rows [128 rank, +128) of super-tile T = tile `rank` of 256-row item 2 unit + T
                 const int item = 2 * unit + T;
                 const int64_t row = ((int64_t)item * 2 + tp.rank) * 128 + r;
-                if (g.enc_mode == 2) encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, row, scratch, T, r);
+                if (g.enc_mode == 2) encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, row, scratch, T, r, busy);
                 else if (item < g.n_items)
                     encode_row_image(g.rays, g.t_vals, g.N, g.S, g.ray_shape, row, const_cast<uint8_t*>(g.enc) + (size_t)item * kEncItemBytes,
-                                     tp.rank, r);
+                                     tp.rank, r, busy);
             }
         }
         tc::fence_proxy_async_all();
@@ -1634,6 +1648,8 @@ static int launch_forward(const char* who, ChainArgs g, int64_t rows, void* stre
     g.rows = rows;
     g.n_items = (int)n_items;
     if (const char* e = getenv("DDNERF_TC_SAVE_ALIAS")) g.save_alias = atoi(e);
+    g.enc_yield = 1;
+    if (const char* e = getenv("DDNERF_TC_ENC_YIELD")) g.enc_yield = atoi(e);
     g.prof = g_prof_buffer;
     if (pair_mode()) {
         const uint64_t enc_blocks = (g.enc_mode == 2 ? (uint64_t)sm_count() * 2 : (uint64_t)n_items) * (kEncItemBytes / 8192);

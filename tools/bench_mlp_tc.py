@@ -127,7 +127,7 @@ def main():
     if args.prof:
         buf = torch.zeros(148 * 8, device="cuda", dtype=torch.int64)
         lib.ddnerf_mlp_tc_set_profile_buffer(_p(buf))
-        runs = [("fwd", fwd)] + ([("dx", dx)] if args.save else [])
+        runs = [("fwd", fwd), ("fwd_rays", fwd_rays)] + ([("dx", dx)] if args.save else [])
         for name, fn in runs:
             buf.zero_()
             fn()
