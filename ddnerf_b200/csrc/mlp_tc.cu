@@ -960,13 +960,21 @@ __device__ __forceinline__ float pack_value(const PackArgs& a, const PackEntry& 
     }
 }
 
+// One block per stage: the [n_total x 32 k] bf16 image is assembled in shared memory (element order chosen so that a warp
+// reads consecutive fp32 parameters: along k for the forward stages, along n for the transposed stages of the dX program)
+// and leaves as 16-byte stores.  Runs after every optimizer step (20 us -> 5 us per network).
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
+    __shared__ __align__(16) uint8_t img[256 * 64];
     const PackEntry E = c_pack.e[blockIdx.x];
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.wimg + E.dst_off);
-    for (int e = threadIdx.x; e < E.n_total * 32; e += blockDim.x) {
-        const int n = e >> 5, kk = e & 31;
-        dst[tc::sw64_off(n, kk) >> 1] = __float2bfloat16_rn(pack_value(a, E, n, E.k0 + kk));
+    const int total = E.n_total * 32;
+    const bool along_n = E.kind == PK_BWD || E.kind == PK_BWD_DIR;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int n = along_n ? e % E.n_total : e >> 5, kk = along_n ? e / E.n_total : e & 31;
+        *reinterpret_cast<__nv_bfloat16*>(img + tc::sw64_off(n, kk)) = __float2bfloat16_rn(pack_value(a, E, n, E.k0 + kk));
     }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(a.wimg + E.dst_off);
+    for (int i = threadIdx.x; i < E.n_total * 4; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(img)[i];
 }
 
 // bias table [16][256]: rows 0..8 = layers_xyz.0-7, fc_feat; row 9 = [layers_dir.0 (128) | fc_alpha];

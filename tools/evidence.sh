@@ -17,9 +17,10 @@ cap() {  # name regex skip extra-args
       python tools/bench_mlp_tc.py --rays 4096 --samples 128 --iters 1 $4 > gpurun_out/${TAG}_ncu_$1.log 2>&1
   python tools/ncu_summary.py /tmp/ncu_$TAG/$1.ncu-rep > gpurun_out/${TAG}_ncu_$1.md 2>> gpurun_out/${TAG}_ncu_$1.log && echo "$1 ok"
 }
-# (ncu matches the function name without template arguments: the chain kernel's launches are, in order,
-#  forward x4 [3 warm-up + 1], then -- with --save -- dX chain x3)
-cap mlp_tc_fwd_nosave "mlp_tc_chain_kernel" 3 ""
-cap mlp_tc_fwd "mlp_tc_chain_kernel" 3 "--save"
-cap mlp_tc_dx "mlp_tc_chain_kernel" 6 "--save"
+# (ncu matches the function name without template arguments: the pair kernel's launches in bench_mlp_tc.py are, in order,
+#  image-fed forward x4 [3 warm-up + 1], ray-fed forward x4, then -- with --save -- dX chain x3)
+cap mlp_tc_pair_fwd_nosave "mlp_tc_pair_kernel" 3 ""
+cap mlp_tc_pair_fwd "mlp_tc_pair_kernel" 3 "--save"
+cap mlp_tc_pair_fwd_rays "mlp_tc_pair_kernel" 7 "--save"
+cap mlp_tc_pair_dx "mlp_tc_pair_kernel" 10 "--save"
 cap mlp_tc_dw "mlp_tc_dw_kernel" 2 "--save"
