@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddnerf_b200.so")
+# (DDNERF_B200_LIB: another build of the same ABI, for A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("DDNERF_B200_LIB") or os.path.join(_HERE, "libddnerf_b200.so")
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int

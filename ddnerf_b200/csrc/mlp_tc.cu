@@ -308,6 +308,23 @@ __device__ void epilogue_bwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, u
     const uint64_t pol_stream = tc::l2_policy_evict_first();
     unsigned long long t_wait = 0, t_busy = 0, n_epi = 0, t_pre = 0, t_work = 0;
 
+    // ReLU mask words of this thread's row and column half for epilogue (unit, e, T); all ones where no mask applies
+    auto fetch_mask = [&](int unit, int e, int T) -> uint4 {
+        uint4 m = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (unit >= tp.n_units) return m;
+        const int ml = P.epis[e].mask_layer;
+        const int tile = tp.tile(unit, T);
+        if (ml < 0 || tile >= n_tiles) return m;
+        const uint32_t* mp = g.mask + (((size_t)ml * n_tiles + tile) * 128 + row) * 8;
+        if (P.epis[e].mode == EPI_BWD_IN) {               // view branch: 2 words per half
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(mp + 2 * hf));
+            m.x = v.x; m.y = v.y;
+        } else {
+            m = __ldg(reinterpret_cast<const uint4*>(mp + 4 * hf));
+        }
+        return m;
+    };
+    uint4 mk_next = fetch_mask(tp.first, 0, 0);
     for (int unit = tp.first; unit < tp.n_units; unit += tp.step) {
         for (int e = 0; e < n_epis; ++e) {
             const Epi E = P.epis[e];
@@ -319,16 +336,14 @@ __device__ void epilogue_bwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, u
                 const uint32_t act_u32 = tc::smem_u32(act_all + T * kActBytes);
                 const uint32_t tmem_row = tmem_q + (uint32_t)T * 256u;
                 const unsigned long long tw0 = g.prof ? clk() : 0;
-                uint32_t mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                if (E.mask_layer >= 0 && tile_ok) {      // this half's ReLU mask words (view branch: 2 words per half)
-                    const uint32_t* mp = g.mask + (((size_t)E.mask_layer * n_tiles + tile_g) * 128 + row) * 8;
-                    if (E.mode == EPI_BWD_IN) {
-                        const uint2 m = __ldg(reinterpret_cast<const uint2*>(mp + 2 * hf));
-                        mk[0] = m.x; mk[1] = m.y;
-                    } else {
-                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(mp + 4 * hf));
-                        mk[0] = m.x; mk[1] = m.y; mk[2] = m.z; mk[3] = m.w;
-                    }
+                // This half's ReLU mask words were requested one epilogue ago: they come from HBM, and the dX chain's epilogues
+                // are busy 3/4 of the time, so a load issued here would put its whole latency between "accumulator ready" and
+                // the first store.  Request the next epilogue's words now.
+                const uint32_t mk[4] = {mk_next.x, mk_next.y, mk_next.z, mk_next.w};
+                {
+                    int nu = unit, ne = e, nT = T ^ 1;
+                    if (T == 1 && ++ne == n_epis) { ne = 0; nu += tp.step; }
+                    mk_next = fetch_mask(nu, ne, nT);
                 }
                 if (E.mode != EPI_BWD_IN) {
                     tc::mbar_wait(&ctl->acc_full[T], (acc_phase >> T) & 1u);
