@@ -38,6 +38,7 @@ SIGNATURES = {
     "ddnerf_raystore_pack": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p]),
     "ddnerf_raystore_gather": (c_i, [c_p, c_l, c_p, c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ddnerf_find_interval": (c_i, [c_p, c_p, c_p, c_l, c_i, c_i, c_p]),
+    "ddnerf_pack_rays": (c_i, [c_p, c_p, c_p, c_f, c_f, c_l, c_p, c_p]),
     "ddnerf_encode": (c_i, [c_p, c_p, c_p, c_l, c_p, c_l, c_l, c_i, c_i, c_p]),
     "ddnerf_mlp_f32_workspace_bytes": (c_l, [c_l]),
     "ddnerf_mlp_f32_forward": (c_i, [ctypes.POINTER(MlpPtrs), c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p, c_p]),

@@ -37,10 +37,38 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ r
     }
 }
 
+// get_rays_batches, models/models.py:144-158: viewdirs = d / ||d||_2, rays = cat(o, d, radius, near, far, viewdirs).
+// One thread per ray instead of eight elementwise / reduce / cat launches; fp32 op by op (this file is built without FMA
+// contraction): squares summed in x, y, z order, IEEE square root and divisions.
+__global__ void __launch_bounds__(256) pack_rays_kernel(const float* __restrict__ ro, const float* __restrict__ rd,
+                                                        const float* __restrict__ rad, float near, float far,
+                                                        float* __restrict__ rays, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float ox = __ldg(ro + 3 * i), oy = __ldg(ro + 3 * i + 1), oz = __ldg(ro + 3 * i + 2);
+    const float dx = __ldg(rd + 3 * i), dy = __ldg(rd + 3 * i + 1), dz = __ldg(rd + 3 * i + 2);
+    const float nrm = __fsqrt_rn(dx * dx + dy * dy + dz * dz);
+    float4* o = reinterpret_cast<float4*>(rays + 12 * i);
+    o[0] = make_float4(ox, oy, oz, dx);
+    o[1] = make_float4(dy, dz, __ldg(rad + i), near);
+    o[2] = make_float4(far, __fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm));
+}
+
 }  // namespace
 }  // namespace ddnerf
 
 using namespace ddnerf;
+
+extern "C" DDNERF_EXPORT int ddnerf_pack_rays(const float* ray_origins, const float* ray_directions, const float* ray_radii,
+                                              float near, float far, int64_t N, float* rays, void* stream) {
+    DDNERF_CHECK_ARG(ray_origins && ray_directions && ray_radii && rays, "pack_rays: null pointer");
+    DDNERF_CHECK_ARG((reinterpret_cast<uintptr_t>(rays) & 15u) == 0, "pack_rays: rays must be 16-byte aligned");
+    if (N == 0) return 0;
+    pack_rays_kernel<<<ceil_div(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ray_origins, ray_directions, ray_radii, near, far,
+                                                                                      rays, N);
+    DDNERF_LAUNCHED("pack_rays", 1);
+    return 0;
+}
 
 extern "C" DDNERF_EXPORT int ddnerf_encode(const float* rays, const float* t_vals, float* enc_out, int64_t ld_enc, float* dir_out,
                              int64_t ld_dir, int64_t N, int S, int ray_shape, void* stream) {

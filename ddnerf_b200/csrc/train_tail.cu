@@ -33,10 +33,12 @@ __global__ void mse_kernel(const float* __restrict__ rgb0, const float* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; }
     __syncthreads();
-    if (threadIdx.x < 2) {
-        float s = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-        atomicAdd(mse_out + threadIdx.x, s * inv);
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+        atomicAdd(mse_out, a * inv);
+        atomicAdd(mse_out + 1, b * inv);
+        atomicAdd(mse_out + 2, coef0 * (a * inv) + coef1 * (b * inv));     // the weighted photometric loss, train_model.py:163
     }
 }
 
@@ -130,7 +132,7 @@ extern "C" DDNERF_EXPORT int ddnerf_mse_loss(const float* rgb0, const float* rgb
                                float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N, void* stream) {
     DDNERF_CHECK_ARG(rgb0 && target && mse_out, "mse_loss: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(mse_out, 0, 2 * sizeof(float), st);
+    cudaMemsetAsync(mse_out, 0, 3 * sizeof(float), st);
     if (N == 0) return 0;
     int64_t n = N * 3;
     int blocks = (int)std::min<int64_t>((n + 255) / 256, 592);

@@ -120,14 +120,7 @@ class GeneralMipNerfModel(torch.nn.Module):
 
     def get_rays_batches(self, ray_origins, ray_directions, ray_rad, mode):
         """models.py:144-162."""
-        viewdirs = ray_directions / ray_directions.norm(p=2, dim=-1).unsqueeze(-1)
-        viewdirs = viewdirs.view((-1, 3))
-        ro = ray_origins.view((-1, 3))
-        rd = ray_directions.reshape((-1, 3))
-        ray_rad = ray_rad.reshape((-1, 1))
-        near = self.cfg.dataset.near * torch.ones_like(rd[..., :1])
-        far = self.cfg.dataset.far * torch.ones_like(rd[..., :1])
-        rays = torch.cat((ro, rd, ray_rad, near, far, viewdirs), dim=-1)
+        rays = ops.pack_rays(ray_origins, ray_directions, ray_rad, self.cfg.dataset.near, self.cfg.dataset.far)
         return get_minibatches(rays, chunksize=getattr(self.cfg.nerf, mode).chunksize)
 
     # ---- nn.Module plumbing the drivers rely on (models.py:164-184) -----------------------

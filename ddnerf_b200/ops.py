@@ -136,6 +136,20 @@ def find_interval(cdf, u):
 RAY_SHAPES = {"cone": 0, "cylinder": 1}
 
 
+def pack_rays(ray_origins, ray_directions, ray_rad, near, far):
+    """get_rays_batches (models.py:144-158): [N,12] rays = (o, d, radius, near, far, d / ||d||) in one launch."""
+    lib = _lib.load()
+    ro = _req(ray_origins, "ray_origins").reshape(-1, 3)
+    rd = _req(ray_directions, "ray_directions").reshape(-1, 3)
+    rad = _req(ray_rad, "ray_rad").reshape(-1)
+    N = ro.shape[0]
+    if rd.shape[0] != N or rad.shape[0] != N:
+        raise RuntimeError("ddnerf_b200: ray_origins, ray_directions and ray_rad disagree on the number of rays")
+    rays = torch.empty(N, 12, device=ro.device, dtype=torch.float32)
+    _lib.check(lib.ddnerf_pack_rays(_p(ro), _p(rd), _p(rad), float(near), float(far), N, _p(rays), _stream()), "pack_rays")
+    return rays
+
+
 def encode(rays, t_vals, ray_shape="cone"):
     """rays [N,12], t_vals [N,S+1] -> the [N*S,123] MLP input of models.py:133."""
     lib = _lib.load()
@@ -383,14 +397,14 @@ def dp_loss(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, 
 # training-step tail
 # ---------------------------------------------------------------------------------------------
 def mse_loss_and_grad(rgb0, rgb1, target, coef0, coef1):
-    """Returns (mse[2], g_rgb0, g_rgb1): the photometric terms of train_model.py:159-163 and the
-    cotangents of coef0*mse0 + coef1*mse1 w.r.t. rgb0 / rgb1."""
+    """Returns (mse[3], g_rgb0, g_rgb1): the photometric terms of train_model.py:159-163 -- mse[0], mse[1] and their
+    weighted sum coef0*mse0 + coef1*mse1 in mse[2] -- and the cotangents of that sum w.r.t. rgb0 / rgb1."""
     lib = _lib.load()
     rgb0, target = _req(rgb0.detach(), "rgb0"), _req(target, "target")
     rgb1 = _opt(None if rgb1 is None else rgb1.detach(), "rgb1")
     g0 = torch.empty_like(rgb0)
     g1 = torch.empty_like(rgb1) if rgb1 is not None else None
-    mse = torch.empty(2, device=rgb0.device, dtype=torch.float32)
+    mse = torch.empty(3, device=rgb0.device, dtype=torch.float32)
     _lib.check(lib.ddnerf_mse_loss(_p(rgb0), _p(rgb1), _p(target), float(coef0), float(coef1), _p(g0), _p(g1), _p(mse),
                                    rgb0.shape[0], _stream()), "mse_loss")
     return mse, g0, g1

@@ -267,8 +267,8 @@ class Trainer:
             frac = (hi - lo) / N
             self.model._rand_base = lo                           # (injected random tensors of the parity tests: this chunk's rows)
             out = self.model.run_iter(ro[lo:hi], rd[lo:hi], rad[lo:hi], mode="train", rgb_target=tgt[lo:hi])
-            mse_c, g0, g1 = ops.mse_loss_and_grad(out[0]["rgb"], out[1]["rgb"], tgt[lo:hi], coef[0] * frac, coef[1] * frac)
-            loss_c = (coef[0] * frac) * mse_c[0] + (coef[1] * frac) * mse_c[1]
+            mse3, g0, g1 = ops.mse_loss_and_grad(out[0]["rgb"], out[1]["rgb"], tgt[lo:hi], coef[0] * frac, coef[1] * frac)
+            mse_c, loss_c = mse3[:2], mse3[2]                    # (views: the kernel also wrote the weighted sum)
             tensors, grads = [out[0]["rgb"], out[1]["rgb"]], [g0, g1]
             if self.is_dd:                                       # train_model.py:163-167
                 dp = out[1]["dp_loss"].mean()
@@ -279,7 +279,10 @@ class Trainer:
             torch.autograd.backward(tensors, grads)
             del out, tensors, grads                              # the chunk's saved activations go back to the allocator
             loss = loss_c if loss is None else loss + loss_c
-            mse = mse_c * frac if mse is None else mse + mse_c * frac
+            if len(spans) == 1:
+                mse = mse_c
+            else:
+                mse = mse_c * frac if mse is None else mse + mse_c * frac
         self.model._rand_base = 0
         for b in self.buckets:
             b.gather_grads()

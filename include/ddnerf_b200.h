@@ -65,6 +65,13 @@ int ddnerf_sample_pdf_mu_sigma_fused(const float* bins, const float* weights, co
 int ddnerf_find_interval(const float* cdf, const float* u, int32_t* idx_out, int64_t N,
                          int S, int n, void* stream);
 
+/* ---- a2: ray packing --------------------------------------------------------------------- */
+/* get_rays_batches, models/models.py:144-158: rays [N,12] = (origin 3, direction 3, radius, near, far,
+ * direction / ||direction||_2) from ray_origins [N,3], ray_directions [N,3], ray_radii [N] and the
+ * dataset's near / far planes.  One launch instead of the reference's norm / div / ones_like / cat. */
+int ddnerf_pack_rays(const float* ray_origins, const float* ray_directions, const float* ray_radii,
+                     float near, float far, int64_t N, float* rays, void* stream);
+
 /* ---- K2: encoding ------------------------------------------------------------------------ */
 /* cast_rays + integrated_pos_enc + positional_encoding of run_network,
  * models/models.py:117-133, general_utils/math_utils.py:7-166, nerf_helpers.py:127-171.
@@ -286,7 +293,7 @@ int ddnerf_dp_loss_backward(const float* t1, const float* t0, const float* w1, c
 
 /* ---- training-step tail on the flat parameter bucket (train_model.py:156-177) ------------ */
 /* loss = sum_j coef_j * mse(rgb_j, target); writes g_rgb_j = coef_j*2*(rgb_j-target)/(3N).
- * mse_out [2].  rgb1/g_rgb1 may be NULL. */
+ * mse_out [3] = {mse(rgb_0), mse(rgb_1), coef_0 mse_0 + coef_1 mse_1}.  rgb1/g_rgb1 may be NULL. */
 int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, float coef0,
                     float coef1, float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N,
                     void* stream);

@@ -816,3 +816,21 @@ def test_full_size_properties(ops):
     (g1,) = torch.autograd.grad((o[0] * ct).sum(), rawg, retain_graph=True)
     (g2,) = torch.autograd.grad((o[0] * ct * 2).sum(), rawg)
     close(g2, 2 * g1, 1e-6, 1e-9)
+
+
+@pytest.mark.parametrize("N", [1, 37, 4096])
+def test_pack_rays_vs_reference_expression(N):
+    """a2, get_rays_batches (models.py:144-158): the one-launch ray packing against the reference's
+    norm / div / ones_like / cat on the CPU: origins, directions, radius, near, far bit-exact, the
+    normalised view directions within one ulp (summation order of the three squares)."""
+    from ddnerf_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    ro, rd = torch.randn(N, 3, generator=g), torch.randn(N, 3, generator=g) * 3.0
+    rad = torch.rand(N, 1, generator=g) * 1e-3
+    near, far = 2.0, 6.0
+    viewdirs = rd / rd.norm(p=2, dim=-1).unsqueeze(-1)
+    ref = torch.cat((ro, rd, rad, near * torch.ones_like(rd[..., :1]), far * torch.ones_like(rd[..., :1]), viewdirs), dim=-1)
+    out = ops.pack_rays(ro.cuda(), rd.cuda(), rad.cuda(), near, far).cpu()
+    assert out.shape == (N, 12)
+    assert torch.equal(out[:, :9], ref[:, :9])
+    assert (out[:, 9:] - ref[:, 9:]).abs().max().item() <= 1.2e-7

@@ -119,6 +119,7 @@ def test_fused_mse_matches_torch(N):
     mse, g0, g1 = ops.mse_loss_and_grad(rgb0, rgb1, tgt, c0, c1)
     assert abs(mse[0].item() - m0.item()) <= 2e-6 * m0.item()
     assert abs(mse[1].item() - m1.item()) <= 2e-6 * m1.item()
+    assert mse.shape == (3,) and abs(mse[2].item() - (c0 * m0 + c1 * m1).item()) <= 2e-6 * (c0 * m0 + c1 * m1).item()
     assert (g0 - rgb0.grad).abs().max().item() <= 1e-6 * rgb0.grad.abs().max().item() + 1e-12
     assert (g1 - rgb1.grad).abs().max().item() <= 1e-6 * rgb1.grad.abs().max().item() + 1e-12
     # single-output form (mip-NeRF validation path)
