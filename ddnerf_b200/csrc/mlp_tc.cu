@@ -397,7 +397,10 @@ __device__ void epilogue_bwd(const ChainArgs& g, const Topo& tp, SmemCtl* ctl, u
                         const uint32_t b2 = act_u32 + 2u * 16384u + (uint32_t)row * 128u;
                         st_shared_v4(b2 + (((0u ^ (uint32_t)row) & 7u) << 4), tc::pack_bf16(gr[3], gr[0]), tc::pack_bf16(gr[1], gr[2]),
                                      tc::pack_bf16(gr[4], gr[5]), 0u);
-                        st_shared_v4(b2 + (((1u ^ (uint32_t)row) & 7u) << 4), 0u, 0u, 0u, 0u);
+                        // the rest of the k-block (columns 136..191) is part of the saved image: zeros, not the previous
+                        // layer's leftovers (they only reach accumulator rows nobody reads, but the image stays deterministic)
+#pragma unroll
+                        for (uint32_t ch = 1; ch < 8; ++ch) st_shared_v4(b2 + (((ch ^ (uint32_t)row) & 7u) << 4), 0u, 0u, 0u, 0u);
                     }
                 } else {
                     const int cb = hf * 128;

@@ -688,3 +688,43 @@ def test_pair_kernels_bit_identical_to_single_cta(N, S, depth_head):
     assert torch.isfinite(b["out"]).all()
     for k in a:
         assert torch.equal(a[k], b[k]), f"{k} differs between the single-CTA and the CTA-pair kernels"
+
+
+@pytest.mark.parametrize("env", [{"DDNERF_TC_PAIR_SHARE": "1"}, {"DDNERF_TC_PSLOTS": "4"}])
+def test_pair_kernel_schedule_knobs_keep_results(env):
+    """The documented schedule knobs of the CTA-pair kernels -- weight stages shared by the two super-tiles (half a layer
+    apart) instead of fetched per super-tile, and a shallower ring -- change the order of loads and waits only: outputs
+    and saved images stay bit-identical to the single-CTA kernels (tools/check_pair.py in a fresh process, because the
+    kernel programs are built once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_pair.py")], env={**os.environ, **env}, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "check_pair: OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pair_dx_chain_on_a_few_ctas():
+    """ddnerf_mlp_tc_backward_dx with max_ctas (the knob that lets a caller share the SMs with another kernel): 2, 5 and 37
+    CTAs (the pair kernels round down to whole pairs) give the same dZ images as the full grid."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200 import _lib, mlp_tc
+    from ddnerf_b200.models import base_architectures as BA
+    from ddnerf_b200.ops import _p, _stream
+    lib = _lib.load()
+    torch.manual_seed(3)
+    rows, C = 256 * 21, 4
+    net = BA.MipNeRFModel(hidden_size=256, max_ipe_deg=16, num_encoding_fn_dir=4, include_input_xyz=False, include_input_dir=True).to("cuda")
+    st = mlp_tc._state(net)
+    st.refresh()
+    mask = torch.randint(0, 255, (lib.ddnerf_mlp_tc_mask_save_bytes(rows),), device="cuda", dtype=torch.uint8)
+    gout = torch.randn(rows, C, device="cuda")
+    outs = []
+    for ctas in (0, 2, 5, 37):
+        dz = torch.zeros(lib.ddnerf_mlp_tc_act_save_bytes(rows), device="cuda", dtype=torch.uint8)
+        _lib.check(lib.ddnerf_mlp_tc_backward_dx(_p(st.wimg), _p(st.bias), _p(gout), rows, C, _p(mask), _p(dz), ctas, _stream()), "dx")
+        torch.cuda.synchronize()
+        outs.append(dz)
+    for dz in outs[1:]:
+        assert torch.equal(dz, outs[0])
