@@ -24,7 +24,7 @@ def reference_root():
 
 
 def stub_missing_driver_deps():
-    """``imageio``, ``matplotlib`` and ``scikit-image`` are not installed in this image.  The reference's data / plot
+    """``imageio``, ``matplotlib``, ``scikit-image`` and ``lpips`` are not installed in this image.  The reference's data / plot
     modules import them at module level; the hot path never calls them.  Register minimal stand-ins (``imageio.imread``
     through PIL so the Blender loader works) unless the real packages exist."""
     def have(name):
@@ -50,9 +50,22 @@ def stub_missing_driver_deps():
             s = types.ModuleType(f"skimage.{sub}")
             setattr(m, sub, s)
             sys.modules[f"skimage.{sub}"] = s
-        sys.modules["skimage.measure"].compare_ssim = None
-        sys.modules["skimage.metrics"].structural_similarity = None
+        # (metrics of eval_nerf.py, outside the hot path: placeholders that keep the driver running)
+        sys.modules["skimage.measure"].compare_ssim = lambda a, b, full=False, **k: (0.0, None) if full else 0.0
+        sys.modules["skimage.metrics"].structural_similarity = lambda a, b, **k: 0.0
         sys.modules["skimage"] = m
+    if not have("lpips"):
+        import torch
+        m = types.ModuleType("lpips")
+
+        class LPIPS:                      # eval_nerf.py:87: the perceptual metric needs downloaded AlexNet weights
+            def __init__(self, *a, **k):
+                pass
+
+            def __call__(self, x, y):
+                return torch.zeros(1, 1, 1, 1)
+        m.LPIPS = LPIPS
+        sys.modules["lpips"] = m
 
 
 def import_reference():

@@ -39,8 +39,8 @@ def _make_blender_scene(root, n_train=3, size=24):
 
 _LAUNCHER = r"""
 import os, sys, runpy
-repo, ref, cfg_path = sys.argv[1], sys.argv[2], sys.argv[3]
-extra = sys.argv[4:]
+repo, ref, script = sys.argv[1], sys.argv[2], sys.argv[3]
+script_args = sys.argv[4:]
 sys.path.insert(0, repo)
 from oracle import reference_loader as RL            # test infrastructure: stubs for imageio / matplotlib / skimage
 RL.stub_missing_driver_deps()
@@ -51,7 +51,7 @@ from models import models
 assert models.DDNerfModel.__module__ == "ddnerf_b200.models.models"
 from ddnerf_b200 import _lib
 before = _lib.load().ddnerf_launch_count()
-sys.argv = [os.path.join(ref, "train_model.py"), "--config", cfg_path] + extra
+sys.argv = [os.path.join(ref, script)] + script_args
 runpy.run_path(sys.argv[0], run_name="__main__")
 print("DDNERF_KERNEL_LAUNCHES", _lib.load().ddnerf_launch_count() - before)
 """
@@ -80,8 +80,8 @@ def test_reference_train_model_runs_unchanged(tmp_path, cfg_name, mlp_mode):
     launcher = tmp_path / "launch.py"
     launcher.write_text(_LAUNCHER)
     env = dict(os.environ, DDNERF_MLP_MODE=mlp_mode)
-    r = subprocess.run([sys.executable, str(launcher), REPO, ref, str(cfg_path)], capture_output=True, text=True,
-                       cwd=str(tmp_path), env=env, timeout=900)
+    r = subprocess.run([sys.executable, str(launcher), REPO, ref, "train_model.py", "--config", str(cfg_path)], capture_output=True,
+                       text=True, cwd=str(tmp_path), env=env, timeout=900)
     tail = (r.stdout[-3000:] + "\n--- stderr ---\n" + r.stderr[-3000:])
     assert r.returncode == 0, tail
     assert "Done!" in r.stdout, tail                                                    # train_model.py:264
@@ -103,8 +103,35 @@ def test_reference_train_model_runs_unchanged(tmp_path, cfg_name, mlp_mode):
     cfg["experiment"]["train_iters"] = 5
     with open(cfg_path, "w") as f:
         yaml.safe_dump(cfg, f)
-    r2 = subprocess.run([sys.executable, str(launcher), REPO, ref, str(cfg_path), "--load-checkpoint",
+    r2 = subprocess.run([sys.executable, str(launcher), REPO, ref, "train_model.py", "--config", str(cfg_path), "--load-checkpoint",
                          str(logdir / "checkpoint.ckpt")], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
     assert r2.returncode == 0 and "Done!" in r2.stdout, r2.stdout[-2000:] + r2.stderr[-3000:]
     ck2 = torch.load(logdir / "checkpoint.ckpt", map_location="cpu", weights_only=False)
     assert ck2["iter"] == 4
+
+
+    # the reference's render driver on that checkpoint (render_video.py:17-112): config.yml + checkpoint.ckpt from the log
+    # directory, load_weights_from_checkpoint, one validation-mode run_iter per render pose, cast_to_disparity_image,
+    # frames into its cv2 video writer and (--save_images) PNGs through imageio
+    r3 = subprocess.run([sys.executable, str(launcher), REPO, ref, "render_video.py", "--logdir", str(logdir), "--save_images", "1"],
+                        capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    tail3 = r3.stdout[-2000:] + "\n--- stderr ---\n" + r3.stderr[-3000:]
+    assert r3.returncode == 0, tail3
+    launches = [int(l.split()[1]) for l in r3.stdout.splitlines() if l.startswith("DDNERF_KERNEL_LAUNCHES")]
+    assert launches and launches[0] > 50, tail3
+    pngs = sorted(os.listdir(logdir / "video" / "images"))
+    assert len(pngs) >= 2 and len(os.listdir(logdir / "video" / "disparity")) == len(pngs), tail3
+    from PIL import Image
+    img = np.array(Image.open(logdir / "video" / "images" / pngs[0]))
+    assert img.shape[:2] == (24, 24) and img.dtype == np.uint8
+
+    # ... and its evaluation driver (eval_nerf.py:20-166): validation-mode run_iter with rgb_target on every validation
+    # pose, save_validation_images over both output dicts, PSNR from the returned rgb (the perceptual / SSIM metrics are
+    # placeholders here: lpips and scikit-image are not installed)
+    r4 = subprocess.run([sys.executable, str(launcher), REPO, ref, "eval_nerf.py", "--logdir", str(logdir)],
+                        capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    tail4 = r4.stdout[-2000:] + "\n--- stderr ---\n" + r4.stderr[-3000:]
+    assert r4.returncode == 0, tail4
+    val = logdir / "validation"
+    assert os.path.exists(val / "results.txt") and os.path.exists(val / "val_image_1" / "rgb_fine.png"), tail4
+    assert "psnr_fine" in open(val / "results.txt").read()
