@@ -1,6 +1,15 @@
 // K1 (bf16 throughput mode): the NeRF MLP of models/base_architectures.py:3-126 as persistent,
-// warp-specialised tcgen05 chain kernels.  A CTA owns a 256-row work item (two 128-row tiles); all
-// GEMMs of the network run back to back with the activations resident on chip:
+// warp-specialised tcgen05 chain kernels; all GEMMs of the network run back to back with the
+// activations resident on chip.  Two variants with bit-identical results share the epilogues, the
+// encoder, the packed weight image and the saved-tile formats:
+//
+//   mlp_tc_pair_kernel  (default): a cluster of two CTAs works on 512 rows = two super-tiles of 256;
+//                    tcgen05.mma.cta_group::2 (M = 256) takes 128 rows of A and half of every weight
+//                    chunk from each CTA, the ring stages arrive by tiled TMA that signals the leader's
+//                    barrier from both CTAs, and the super-tiles run a whole layer apart (see mlp_tc.cuh
+//                    and the section "CTA-pair variant" below);
+//   mlp_tc_chain_kernel (DDNERF_TC_PAIR=0 / ddnerf_mlp_tc_set_pair_mode(0)): one CTA owns a 256-row work
+//                    item (two 128-row tiles), described next.
 //
 //   producer warp  : walks the static load program, streaming 16 KB weight stages (and the encoded
 //                    xyz / view-direction blocks) from L2 into a 6-slot shared-memory ring with
