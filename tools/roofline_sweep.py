@@ -113,6 +113,29 @@ def main():
                 _lib.check(lib.ddnerf_dp_loss_backward(_p(t1), _p(t0), _p(w1), _p(w), _p(mus), _p(sig), _p(lt), _p(pin), 0,
                                                        _p(g_one), _p(dp_scratch), _p(g_w0), _p(g_mu), _p(g_sg), N, S, S,
                                                        _stream()), "dp_loss_backward")
+            # round 2: the fused DDNeRF coarse glue (models.py:242-273 as one kernel each way), the resampler and the
+            # dp-loss that evaluate the two tails per cell themselves
+            raw6s = raw6 * 0.5
+            dd_out = ops.composite_dd(raw6s, t0, rays[:, 3:6], noise, 1.0, False, True, 0.01)
+            w_dd, mus_dd, sig_dd = dd_out[3], dd_out[6], dd_out[7]
+            t1f = ops.sample_pdf_mu_sigma_fused(t0, w_dd, mus_dd, sig_dd, 1.4, S + 1, True, near, far, u)
+            w1f = ops.composite(raw, t1f, rays[:, 3:6], noise, 1.0, None, False, True, False)[3]
+            g_rgb3, g_n = torch.randn(N, 3, device=dev, generator=g), torch.randn(N, device=dev, generator=g)
+            g_ns, g_reg = torch.randn(N, S, device=dev, generator=g), torch.ones(4, device=dev)
+            g_raw6 = torch.empty(N, S, 6, device=dev)
+            dd_gs = [g_rgb3, None, None, g_ns, g_n, None, g_ns, g_ns, g_reg]
+
+            def composite_dd_bwd():
+                _lib.check(lib.ddnerf_composite_dd_backward(_p(raw6s), _p(t0), _p(rd), rd.stride(0), _p(noise), 1.0, 0, 1, 0.01,
+                                                            *[_p(x) for x in dd_gs], _p(g_raw6), N, S, _stream()), "composite_dd_backward")
+            dp_scratch2 = torch.zeros(4 + 2 * N, device=dev)
+            _lib.check(lib.ddnerf_dp_loss_forward(_p(t1f), _p(t0), _p(w1f), _p(w_dd), _p(mus_dd), _p(sig_dd), None, None, 1, _p(dp_out),
+                                                  _p(dp_scratch2), N, S, S, _stream()), "dp_loss_forward")
+
+            def dp_bwd_tails():
+                _lib.check(lib.ddnerf_dp_loss_backward(_p(t1f), _p(t0), _p(w1f), _p(w_dd), _p(mus_dd), _p(sig_dd), None, None, 1,
+                                                       _p(g_one), _p(dp_scratch2), _p(g_w0), _p(g_mu), _p(g_sg), N, S, S,
+                                                       _stream()), "dp_loss_backward")
             R = N * S
             # name, callable, algorithmic bytes
             stages = [
@@ -128,6 +151,16 @@ def main():
                 ("dp_loss fwd", lambda: ops.dp_loss(t1, t0, w1, w, mus, sig, lt, pin, False), R * 32),
                 ("dp_loss bwd", dp_bwd, R * (32 + 12)),
                 ("encode -> bf16 operand images", lambda: mlp_tc.encode_img(rays, t0), R * (4 + 256) + N * 48),
+                # raw6 + t + noise in, weights + mus + sigmas out (+ per-ray maps)
+                ("composite_dd fwd (DDNeRF coarse: compositor + mu/sigma head + regularisers)",
+                 lambda: ops.composite_dd(raw6s, t0, rays[:, 3:6], noise, 1.0, False, True, 0.01), R * (24 + 4 + 4 + 12) + N * (12 + 28)),
+                # raw6 + t + noise + three [N,S] cotangents in, g_raw6 out
+                ("composite_dd bwd", composite_dd_bwd, R * (24 + 4 + 4 + 12 + 24) + N * (12 + 16)),
+                # bins, weights, mus, sigmas, u in; samples out (tails evaluated per cell in the kernel)
+                ("sample_pdf_mu_sigma fused (tails in kernel)",
+                 lambda: ops.sample_pdf_mu_sigma_fused(t0, w_dd, mus_dd, sig_dd, 1.4, S + 1, True, near, far, u), 4 * N * (6 * S + 3)),
+                ("dp_loss fwd (tails in kernel)", lambda: ops.dp_loss(t1f, t0, w1f, w_dd, mus_dd, sig_dd, None, None, True), R * 24),
+                ("dp_loss bwd (tails in kernel)", dp_bwd_tails, R * (24 + 12)),
             ]
             fl = flush if R * 28 < 512 * 1024 * 1024 else None
             for name, fn, nbytes in stages:
