@@ -73,6 +73,8 @@ SIGNATURES = {
     "ddnerf_composite_dd_backward": (c_i, [c_p, c_p, c_p, c_l, c_p, c_f, c_i, c_i, c_f] + [c_p] * 10 + [c_l, c_i, c_p]),
     "ddnerf_dp_loss_forward": (c_i, [c_p] * 8 + [c_i, c_p, c_p, c_l, c_i, c_i, c_p]),
     "ddnerf_dp_loss_backward": (c_i, [c_p] * 8 + [c_i] + [c_p] * 5 + [c_l, c_i, c_i, c_p]),
+    "ddnerf_dp_loss_total_forward": (c_i, [c_p] * 8 + [c_i, c_f, c_p, c_p, c_p, c_l, c_i, c_i, c_p]),
+    "ddnerf_dp_loss_total_backward": (c_i, [c_p] * 8 + [c_i, c_f] + [c_p] * 6 + [c_l, c_i, c_i, c_p]),
     "ddnerf_mse_loss": (c_i, [c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_p]),
     "ddnerf_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_l, c_f, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_i, c_f, c_p]),
     "ddnerf_adam_step_dev": (c_i, [c_p, c_p, c_p, c_p, c_l, c_p, c_p]),

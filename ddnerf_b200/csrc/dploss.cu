@@ -48,6 +48,24 @@ __device__ __forceinline__ int count_lt(const float* v, int len, float x) {
 
 struct RayState { float Z0, Z1, Zq; bool relevant; };
 
+// The loss as DDNerfModel.predict consumes it (models.py:287-289): kl * scale + mus_reg + sig_reg with scale = the number
+// of fine cells and the two regularisers in regs[2], regs[3] (what ddnerf_composite_dd_forward wrote).  regs == NULL and
+// scale == 1: the plain kl_div of dd_utils.py.  Folding it here removes three elementwise launches from the forward and
+// the slice / mul / add chain (eight launches) from the backward of a training step.
+struct DpTotal { float scale; const float* regs; float* g_regs; };
+__device__ __forceinline__ float dp_total(const DpTotal& tt, float kl) {
+    float v = kl * tt.scale;
+    if (tt.regs) { v = v + __ldg(tt.regs + 2); v = v + __ldg(tt.regs + 3); }
+    return v;
+}
+// cotangent of regs = {mus_loss, sig_loss, mus_reg, sig_reg}: written by one thread of the backward launch
+__device__ __forceinline__ void dp_total_g_regs(const DpTotal& tt, const float* g_loss) {
+    if (tt.g_regs && blockIdx.x == 0 && threadIdx.x == 0) {
+        const float g = __ldg(g_loss);
+        tt.g_regs[0] = 0.f; tt.g_regs[1] = 0.f; tt.g_regs[2] = g; tt.g_regs[3] = g;
+    }
+}
+
 // Shared layout per warp (floats): p0[S0] cum[S0+1] cdf[S0+1] t0s[S0+1] E[S1+1]  (+ backward arrays)
 struct Smem {
     float *p0, *cum, *cdf, *t0s, *E;
@@ -114,7 +132,7 @@ __device__ RayState ray_forward(const DpArgs& a, const Smem& sm, int64_t ray, in
     return rs;
 }
 
-__global__ void dp_loss_fwd_kernel(DpArgs a, float* __restrict__ loss_out, float* __restrict__ scratch, int per_warp) {
+__global__ void dp_loss_fwd_kernel(DpArgs a, DpTotal tt, float* __restrict__ loss_out, float* __restrict__ scratch, int per_warp) {
     extern __shared__ float smem[];
     __shared__ float blk[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,15 +161,16 @@ __global__ void dp_loss_fwd_kernel(DpArgs a, float* __restrict__ loss_out, float
         if (ticket == gridDim.x - 1) {
             __threadfence();
             float sum = atomicAdd(scratch + 0, 0.f), cnt = atomicAdd(scratch + 1, 0.f);
-            *loss_out = cnt > 0.f ? sum / (cnt * (float)a.S1) : 0.f;   // reduction='mean' over kept rays x S1
+            *loss_out = dp_total(tt, cnt > 0.f ? sum / (cnt * (float)a.S1) : 0.f);   // reduction='mean' over kept rays x S1
         }
     }
 }
 
-__global__ void dp_loss_bwd_kernel(DpArgs a, const float* __restrict__ g_loss, const float* __restrict__ scratch,
+__global__ void dp_loss_bwd_kernel(DpArgs a, DpTotal tt, const float* __restrict__ g_loss, const float* __restrict__ scratch,
                                    float* __restrict__ g_w0, float* __restrict__ g_mus0, float* __restrict__ g_sig0,
                                    int per_warp) {
     extern __shared__ float smem[];
+    dp_total_g_regs(tt, g_loss);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= a.N) return;
@@ -168,7 +187,7 @@ __global__ void dp_loss_bwd_kernel(DpArgs a, const float* __restrict__ g_loss, c
         for (int i = lane; i < S0; i += 32) { g_w0[ray * S0 + i] = 0.f; g_mus0[ray * S0 + i] = 0.f; g_sig0[ray * S0 + i] = 0.f; }
         return;
     }
-    const float scale = __ldg(g_loss) / (cnt * (float)S1);
+    const float scale = __ldg(g_loss) * tt.scale / (cnt * (float)S1);
     for (int i = lane; i < S0; i += 32) { gcdf[i] = 0.f; gp0[i] = 0.f; gmu[i] = 0.f; gsg[i] = 0.f; }
     if (lane == 0) gcdf[S0] = 0.f;
     __syncwarp();
@@ -431,7 +450,7 @@ __global__ void __launch_bounds__(128) dp_loss_fwd_fast_kernel(DpArgs a, float* 
 }
 
 __global__ void __launch_bounds__(1024) dp_loss_finish_kernel(float* __restrict__ scratch, float* __restrict__ loss_out,
-                                                               int64_t N, int S1) {
+                                                               int64_t N, int S1, DpTotal tt) {
     __shared__ float ssum[32], scnt[32];
     float sum = 0.f, cnt = 0.f;
     for (int64_t i = threadIdx.x; i < N; i += 1024) { sum += scratch[4 + i]; cnt += scratch[4 + N + i]; }
@@ -442,18 +461,19 @@ __global__ void __launch_bounds__(1024) dp_loss_finish_kernel(float* __restrict_
         sum = group_sum<32>(ssum[threadIdx.x]); cnt = group_sum<32>(scnt[threadIdx.x]);
         if (threadIdx.x == 0) {
             scratch[0] = sum; scratch[1] = cnt;
-            *loss_out = cnt > 0.f ? sum / (cnt * (float)S1) : 0.f;     // reduction='mean' over kept rays x S1
+            *loss_out = dp_total(tt, cnt > 0.f ? sum / (cnt * (float)S1) : 0.f);     // reduction='mean' over kept rays x S1
         }
     }
 }
 
 template <int G, int C, int K>
-__global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, const float* __restrict__ g_loss,
+__global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, DpTotal tt, const float* __restrict__ g_loss,
                                                                 const float* __restrict__ scratch,
                                                                 float* __restrict__ g_w0, float* __restrict__ g_mus0,
                                                                 float* __restrict__ g_sig0, int per_ray) {
     extern __shared__ __align__(16) float smem[];
     constexpr int P = G * C;
+    dp_total_g_regs(tt, g_loss);
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     int64_t ray = (int64_t)blockIdx.x * (blockDim.x / G) + grp;
     const bool valid = ray < a.N;
@@ -466,7 +486,7 @@ __global__ void __launch_bounds__(128) dp_loss_bwd_fast_kernel(DpArgs a, const f
     RayState rs = sm.forward(a, ray, gl, fs);             // (its __syncwarp()s order the zero fill)
     const float cnt = __ldg(scratch + 1);
     const bool live = rs.relevant && cnt > 0.f;           // uniform over the lane group
-    const float scale = live ? __ldg(g_loss) / (cnt * (float)S1) : 0.f;
+    const float scale = live ? __ldg(g_loss) * tt.scale / (cnt * (float)S1) : 0.f;
     const float zr = rs.Zq / rs.Z1, sz = scale / rs.Zq;
     float carry = 0.f;                                    // gq of the previous chunk's last edge
 #pragma unroll
@@ -567,16 +587,19 @@ int warps_for(size_t per_warp_bytes) {
 
 using namespace ddnerf;
 
-extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float* t0, const float* w1, const float* w0,
-                                      const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
-                                      int blender, float* loss_out, float* scratch, int64_t N, int S0, int S1,
-                                      void* stream) {
+static int dp_loss_forward_impl(const float* t1, const float* t0, const float* w1, const float* w0, const float* mus0,
+                                const float* sigmas0, const float* lt0, const float* pin0, int blender, DpTotal tt,
+                                float* loss_out, float* scratch, int64_t N, int S0, int S1, void* stream) {
     DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && loss_out && scratch, "dp_loss_forward: null pointer");
     DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_forward: lt0 and pin0 go together (both NULL: computed in the kernel)");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_forward: S0=%d S1=%d unsupported", S0, S1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st);
-    if (N == 0) { cudaMemsetAsync(loss_out, 0, sizeof(float), st); return 0; }
+    if (N == 0) {                                           // no rays: kl = 0 (and the header the backward reads)
+        cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st);
+        dp_loss_finish_kernel<<<1, 1024, 0, st>>>(scratch, loss_out, 0, S1, tt);
+        DDNERF_LAUNCHED("dp_loss_forward", 1);
+        return 0;
+    }
     DpArgs a{t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, N, S0, S1};
     bool fast = dispatch_fast(S0, S1, [&](auto g, auto c, auto kk) {
         constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
@@ -586,7 +609,7 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float
         auto kern = dp_loss_fwd_fast_kernel<G, C, K>;
         if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         kern<<<ceil_div(N, 128 / G), 128, bytes, st>>>(a, scratch, per_ray);
-        dp_loss_finish_kernel<<<1, 1024, 0, st>>>(scratch, loss_out, N, S1);
+        dp_loss_finish_kernel<<<1, 1024, 0, st>>>(scratch, loss_out, N, S1, tt);   // (writes the header: no memset needed)
         ddnerf::count_launches(1);
         return true;
     });
@@ -594,24 +617,32 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float
         int per_warp = Smem::floats(S0, S1);
         int wpb = warps_for(per_warp * sizeof(float));
         DDNERF_CHECK_ARG(wpb >= 1, "dp_loss_forward: shapes need too much shared memory");
-        dp_loss_fwd_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(a, loss_out, scratch,
+        cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st);                        // the generic kernel accumulates with atomics
+        dp_loss_fwd_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(a, tt, loss_out, scratch,
                                                                                                        per_warp);
     }
     DDNERF_LAUNCHED("dp_loss_forward", 1);
     return 0;
 }
 
-extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const float* t0, const float* w1, const float* w0,
-                                       const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
-                                       int blender, const float* g_loss, const float* scratch, float* g_w0,
-                                       float* g_mus0, float* g_sigmas0, int64_t N, int S0, int S1, void* stream) {
+static int dp_loss_backward_impl(const float* t1, const float* t0, const float* w1, const float* w0, const float* mus0,
+                                 const float* sigmas0, const float* lt0, const float* pin0, int blender, DpTotal tt,
+                                 const float* g_loss, const float* scratch, float* g_w0, float* g_mus0, float* g_sigmas0,
+                                 int64_t N, int S0, int S1, void* stream) {
     DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && g_loss && scratch && g_w0 && g_mus0 && g_sigmas0,
                      "dp_loss_backward: null pointer");
     DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_backward: lt0 and pin0 go together");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_backward: S0=%d S1=%d unsupported", S0, S1);
-    if (N == 0) return 0;
-    DpArgs a{t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, N, S0, S1};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 0) {
+        if (tt.g_regs) {                                    // the regularisers still receive the cotangent
+            cudaMemsetAsync(tt.g_regs, 0, 2 * sizeof(float), st);
+            cudaMemcpyAsync(tt.g_regs + 2, g_loss, sizeof(float), cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(tt.g_regs + 3, g_loss, sizeof(float), cudaMemcpyDeviceToDevice, st);
+        }
+        return 0;
+    }
+    DpArgs a{t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, N, S0, S1};
     bool fast = dispatch_fast(S0, S1, [&](auto g, auto c, auto kk) {
         constexpr int G = decltype(g)::value, C = decltype(c)::value, K = decltype(kk)::value;
         const int per_ray = CellDp<G, C, K, true>::floats(S1);
@@ -619,7 +650,7 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const floa
         if (bytes > 200 * 1024) return false;
         auto kern = dp_loss_bwd_fast_kernel<G, C, K>;
         if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        kern<<<ceil_div(N, 128 / G), 128, bytes, st>>>(a, g_loss, scratch, g_w0, g_mus0, g_sigmas0, per_ray);
+        kern<<<ceil_div(N, 128 / G), 128, bytes, st>>>(a, tt, g_loss, scratch, g_w0, g_mus0, g_sigmas0, per_ray);
         return true;
     });
     if (!fast) {
@@ -627,8 +658,43 @@ extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const floa
         int wpb = warps_for(per_warp * sizeof(float));
         DDNERF_CHECK_ARG(wpb >= 1, "dp_loss_backward: shapes need too much shared memory");
         dp_loss_bwd_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(
-            a, g_loss, scratch, g_w0, g_mus0, g_sigmas0, per_warp);
+            a, tt, g_loss, scratch, g_w0, g_mus0, g_sigmas0, per_warp);
     }
     DDNERF_LAUNCHED("dp_loss_backward", 1);
     return 0;
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_dp_loss_forward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                      const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
+                                      int blender, float* loss_out, float* scratch, int64_t N, int S0, int S1,
+                                      void* stream) {
+    return dp_loss_forward_impl(t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, DpTotal{1.0f, nullptr, nullptr}, loss_out,
+                                scratch, N, S0, S1, stream);
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_dp_loss_backward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                       const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
+                                       int blender, const float* g_loss, const float* scratch, float* g_w0,
+                                       float* g_mus0, float* g_sigmas0, int64_t N, int S0, int S1, void* stream) {
+    return dp_loss_backward_impl(t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, DpTotal{1.0f, nullptr, nullptr}, g_loss,
+                                 scratch, g_w0, g_mus0, g_sigmas0, N, S0, S1, stream);
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_dp_loss_total_forward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                            const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
+                                            int blender, float scale, const float* regs, float* loss_out, float* scratch,
+                                            int64_t N, int S0, int S1, void* stream) {
+    DDNERF_CHECK_ARG(regs, "dp_loss_total_forward: regs is NULL");
+    return dp_loss_forward_impl(t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, DpTotal{scale, regs, nullptr}, loss_out,
+                                scratch, N, S0, S1, stream);
+}
+
+extern "C" DDNERF_EXPORT int ddnerf_dp_loss_total_backward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                             const float* mus0, const float* sigmas0, const float* lt0, const float* pin0,
+                                             int blender, float scale, const float* g_loss, const float* scratch,
+                                             float* g_w0, float* g_mus0, float* g_sigmas0, float* g_regs, int64_t N, int S0,
+                                             int S1, void* stream) {
+    DDNERF_CHECK_ARG(g_regs, "dp_loss_total_backward: g_regs is NULL");
+    return dp_loss_backward_impl(t1, t0, w1, w0, mus0, sigmas0, lt0, pin0, blender, DpTotal{scale, nullptr, g_regs}, g_loss,
+                                 scratch, g_w0, g_mus0, g_sigmas0, N, S0, S1, stream);
 }

@@ -21,6 +21,11 @@ from ..general_utils.nerf_helpers import get_embedding_function, get_minibatches
 from ..general_utils.math_utils import approximate_cdf, integrated_pos_enc
 
 
+def _is_blender_type(cfg):
+    """dd_utils.py:12 (the row filter of the dp-loss looks at the dataset type only)."""
+    return cfg.dataset.type.lower() == "blender"
+
+
 class GeneralMipNerfModel(torch.nn.Module):
     """models.py:9-184."""
 
@@ -82,6 +87,30 @@ class GeneralMipNerfModel(torch.nn.Module):
     def _mode_cfg(self, mode):
         return getattr(self.cfg.nerf, mode)
 
+    def _draw_randoms(self, N, mode, device):
+        """The four random tensors the reference draws inside one predict() (samplers.py:57 t_rand [N,S0+1], :102 / :165
+        u_rand [N,S1+1], volume_rendering_utils.py:31 noise0 [N,S0] and noise1 [N,S1]): injected ones are used as they are,
+        the rest comes from ONE torch.rand and ONE torch.randn call per chunk (contiguous halves of a flat draw) instead
+        of four generator launches.  None where the mode does not use the tensor."""
+        mcfg = self._mode_cfg(mode)
+        S0, S1 = mcfg.num_coarse, mcfg.num_fine
+        r = {k: self._rnd(k) for k in ("t_rand", "u_rand", "noise0", "noise1")}
+        uni = [(k, n) for k, n in (("t_rand", S0 + 1), ("u_rand", S1 + 1)) if bool(mcfg.perturb) and r[k] is None]
+        nor = [(k, n) for k, n in (("noise0", S0), ("noise1", S1)) if mcfg.radiance_field_noise_std > 0.0 and r[k] is None]
+        for group, draw in ((uni, torch.rand), (nor, torch.randn)):
+            if not group:
+                continue
+            flat = draw(N * sum(n for _, n in group), dtype=torch.float32, device=device)
+            off = 0
+            for k, n in group:
+                r[k] = flat[off:off + N * n].view(N, n)
+                off += N * n
+        if not bool(mcfg.perturb):
+            r["t_rand"] = r["u_rand"] = None
+        if not mcfg.radiance_field_noise_std > 0.0:
+            r["noise0"] = r["noise1"] = None
+        return r
+
     def predict(self, ray_batch, mode, depth_analysis_validation, rgb_target=None):
         """models.py:75-114."""
         if depth_analysis_validation:
@@ -92,16 +121,17 @@ class GeneralMipNerfModel(torch.nn.Module):
         mcfg = self._mode_cfg(mode)
         ret = {}
         t_vals = weights = None
+        rnd = self._draw_randoms(ray_batch.shape[0], mode, ray_batch.device)
         for i in range(2):
             if i == 0:
-                t_vals = sample_first_cycle(self.cfg, near, far, mode, t_rand=self._rnd("t_rand"))
+                t_vals = sample_first_cycle(self.cfg, near, far, mode, t_rand=rnd["t_rand"])
             else:
                 t_vals = sample_pdf(t_vals, weights, mcfg.num_fine + 1, self.cfg, det=(mcfg.perturb == 0.0),
-                                    rand=self._rnd("u_rand")).detach()
+                                    rand=rnd["u_rand"]).detach()
             radiance_field = self.run_network(ray_batch, t_vals, self.coarse, mode)
             rgb, disp, acc, weights, depth, _, _ = volume_render_radiance_field(
                 radiance_field, t_vals, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
-                white_background=mcfg.white_background, cfg=self.cfg, noise=self._rnd(f"noise{i}"), want_rgb=False)
+                white_background=mcfg.white_background, cfg=self.cfg, noise=rnd[f"noise{i}"], want_rgb=False)
             ret[i] = {"rgb": rgb, "disp": disp, "acc": acc, "weights": weights, "depth": depth}
             self._record_t(i, t_vals)
         return ret
@@ -170,15 +200,12 @@ class DDNerfModel(GeneralMipNerfModel):
         # network -- sigmoid of the (mu, sigma) head, regulariser sums, compositing with the corrected depth -- is ONE
         # kernel (ops.composite_dd); the tails Phi((0-mu)/sigma), Phi((1-mu)/sigma) and their smoothed versions are
         # evaluated per cell inside the resampler / dp-loss kernels that consume them.
-        t0 = sample_first_cycle(self.cfg, near, far, mode, t_rand=self._rnd("t_rand"))
+        rnd = self._draw_randoms(ray_batch.shape[0], mode, ray_batch.device)
+        t0 = sample_first_cycle(self.cfg, near, far, mode, t_rand=rnd["t_rand"])
         rf0 = self.run_network(ray_batch, t0, self.coarse, mode)
-        noise0 = self._rnd("noise0")
         std = mcfg.radiance_field_noise_std
-        if std > 0.0 and noise0 is None:
-            noise0 = torch.randn(rf0.shape[:2], dtype=rf0.dtype, device=rf0.device)      # volume_rendering_utils.py:31
         rgb, disp, acc, w0, depth, cdisp, mus, sigmas, regs = ops.composite_dd(
-            rf0, t0, rd, noise0 if std > 0.0 else None, std, mcfg.white_background, _is_blender(self.cfg),
-            tp.dist_reg_coeficient)
+            rf0, t0, rd, rnd["noise0"], std, mcfg.white_background, _is_blender(self.cfg), tp.dist_reg_coeficient)
         mus_loss, sig_loss, mus_reg, sig_reg = regs[0:1], regs[1:2], regs[2:3], regs[3:4]
         if self.record_distributions:                           # models.py:292-300 (mask from pass 0)
             smoothed_sigmas = sigmas * tp.gaussian_smooth_factor
@@ -191,20 +218,18 @@ class DDNerfModel(GeneralMipNerfModel):
                   "sig_reg": sig_reg}
 
         # ---- pass 1: fine network on depth-distribution samples (models.py:225-237, 276-289)
-        det = mcfg.perturb == 0.0
-        u_rand = None if det else self._rnd("u_rand")
-        if not det and u_rand is None:
-            u_rand = torch.rand(w0.shape[0], mcfg.num_fine + 1, device=w0.device)          # samplers.py:165
         t1 = ops.sample_pdf_mu_sigma_fused(t0, w0, mus, sigmas, tp.gaussian_smooth_factor, mcfg.num_fine + 1,
-                                           tp.pdf_padding, self.cfg.dataset.near, self.cfg.dataset.far, u_rand)
+                                           tp.pdf_padding, self.cfg.dataset.near, self.cfg.dataset.far, rnd["u_rand"])
         self._record_t(0, t0)
         self._record_t(1, t1)
         rf1 = self.run_network(ray_batch, t1, self.fine, mode)
         rgb1, disp1, acc1, w1, depth1, _, _ = volume_render_radiance_field(
             rf1, t1, rd, radiance_field_noise_std=mcfg.radiance_field_noise_std,
-            white_background=mcfg.white_background, mus=None, cfg=self.cfg, noise=self._rnd("noise1"), want_rgb=False)
-        dp_loss = estimate_dp_loss(t1, t0, w1.detach(), w0, mus, sigmas, None, None, self.cfg) * (t1.shape[1] - 1)
-        dp_loss = dp_loss + mus_reg + sig_reg                    # [1] (mus_reg / sig_reg are [1] views of regs)
+            white_background=mcfg.white_background, mus=None, cfg=self.cfg, noise=rnd["noise1"], want_rgb=False)
+        # models.py:287-289: estimate_dp_loss(...) * (S1) + mus_reg + sig_reg, [1]; the finishing kernel of the loss adds the
+        # terms and its backward kernel returns the cotangent of regs (no slice / mul / add launches either way)
+        dp_loss = ops.dp_loss_total(t1.detach(), t0.detach(), w1.detach(), w0, mus, sigmas, None, None, _is_blender_type(self.cfg),
+                                    regs, t1.shape[1] - 1)
         ret[1] = {"rgb": rgb1, "disp": disp1, "acc": acc1, "weights": w1, "depth": depth1, **rec, "dp_loss": dp_loss,
                   "corrected_disp_map": None}
         return ret

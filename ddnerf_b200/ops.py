@@ -357,8 +357,11 @@ def composite_dd(raw6, t_vals, rd, noise=None, noise_std=0.0, white_background=F
 # K5 depth-distribution loss
 # ---------------------------------------------------------------------------------------------
 class _DpLoss(torch.autograd.Function):
+    """regs is None: kl_div of dd_utils.py:6-78.  regs [4] (+ scale): the loss term of models.py:287-289,
+    kl * scale + regs[2] + regs[3], with the cotangent of regs returned too."""
+
     @staticmethod
-    def forward(ctx, t1, t0, w1, w0, mus0, sig0, lt0, pin0, blender):
+    def forward(ctx, t1, t0, w1, w0, mus0, sig0, lt0, pin0, blender, regs, scale):
         lib = _lib.load()
         t1, t0, w1, w0 = _req(t1, "t_vals_1"), _req(t0, "t_vals_0"), _req(w1, "pdf_1"), _req(w0, "pdf_0")
         mus0, sig0 = _req(mus0, "mus_0"), _req(sig0, "sigmas_0")
@@ -366,31 +369,53 @@ class _DpLoss(torch.autograd.Function):
             raise RuntimeError("ddnerf_b200: dp_loss takes left_tails_0 and part_inside_0 together (both None: computed in the kernel)")
         lt0, pin0 = _opt(lt0, "left_tails_0"), _opt(pin0, "part_inside")
         N, S0, S1 = w0.shape[0], w0.shape[1], w1.shape[1]
-        loss = torch.empty((), device=w0.device, dtype=torch.float32)
         scratch = torch.empty(4 + 2 * N, device=w0.device, dtype=torch.float32)      # header + per-ray KL and relevance
-        _lib.check(lib.ddnerf_dp_loss_forward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
-                                              int(bool(blender)), _p(loss), _p(scratch), N, S0, S1, _stream()), "dp_loss_forward")
+        if regs is None:
+            loss = torch.empty((), device=w0.device, dtype=torch.float32)
+            _lib.check(lib.ddnerf_dp_loss_forward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
+                                                  int(bool(blender)), _p(loss), _p(scratch), N, S0, S1, _stream()), "dp_loss_forward")
+        else:
+            regs = _req(regs, "regs")
+            if regs.numel() != 4:
+                raise RuntimeError("ddnerf_b200: dp_loss_total needs regs = [mus_loss, sig_loss, mus_reg, sig_reg]")
+            loss = torch.empty(1, device=w0.device, dtype=torch.float32)
+            _lib.check(lib.ddnerf_dp_loss_total_forward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
+                                                        int(bool(blender)), float(scale), _p(regs), _p(loss), _p(scratch), N,
+                                                        S0, S1, _stream()), "dp_loss_total_forward")
         ctx.save_for_backward(t1, t0, w1, w0, mus0, sig0, lt0, pin0, scratch)
-        ctx.cfg = (bool(blender), N, S0, S1)
+        ctx.cfg = (bool(blender), N, S0, S1, regs is not None, float(scale))
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
         lib = _lib.load()
         t1, t0, w1, w0, mus0, sig0, lt0, pin0, scratch = ctx.saved_tensors
-        blender, N, S0, S1 = ctx.cfg
+        blender, N, S0, S1, total, scale = ctx.cfg
         g_loss = g_loss.contiguous().float()
         g_w0, g_mu, g_sg = torch.empty_like(w0), torch.empty_like(w0), torch.empty_like(w0)
-        _lib.check(lib.ddnerf_dp_loss_backward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
-                                               int(blender), _p(g_loss), _p(scratch), _p(g_w0), _p(g_mu), _p(g_sg), N, S0, S1,
-                                               _stream()), "dp_loss_backward")
-        return None, None, None, g_w0, g_mu, g_sg, None, None, None
+        if not total:
+            _lib.check(lib.ddnerf_dp_loss_backward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
+                                                   int(blender), _p(g_loss), _p(scratch), _p(g_w0), _p(g_mu), _p(g_sg), N, S0, S1,
+                                                   _stream()), "dp_loss_backward")
+            return None, None, None, g_w0, g_mu, g_sg, None, None, None, None, None
+        g_regs = torch.empty(4, device=w0.device, dtype=torch.float32)
+        _lib.check(lib.ddnerf_dp_loss_total_backward(_p(t1), _p(t0), _p(w1), _p(w0), _p(mus0), _p(sig0), _p(lt0), _p(pin0),
+                                                     int(blender), scale, _p(g_loss), _p(scratch), _p(g_w0), _p(g_mu), _p(g_sg),
+                                                     _p(g_regs), N, S0, S1, _stream()), "dp_loss_total_backward")
+        return None, None, None, g_w0, g_mu, g_sg, None, None, None, g_regs, None
 
 
 def dp_loss(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender):
     """kl_div(log q, p1, 'mean') of dd_utils.py:6-78.  Gradients flow to pdf_0, mus_0, sigmas_0.  With
     left_tails_0 = part_inside_0 = None the kernels evaluate the two tails themselves (models.py:254-258)."""
-    return _DpLoss.apply(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender)
+    return _DpLoss.apply(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender, None, 1.0)
+
+
+def dp_loss_total(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender, regs, scale):
+    """models.py:287-289 in one call: ``(estimate_dp_loss(...) * scale + mus_reg + sig_reg).unsqueeze(0)`` with
+    ``regs = [mus_loss, sig_loss, mus_reg, sig_reg]`` (the 4-vector composite_dd returns).  Returns a [1] tensor;
+    gradients flow to pdf_0, mus_0, sigmas_0 and regs."""
+    return _DpLoss.apply(t1, t0, pdf_1, pdf_0, mus_0, sigmas_0, left_tails_0, part_inside_0, blender, regs, scale)
 
 
 # ---------------------------------------------------------------------------------------------

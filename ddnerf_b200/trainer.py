@@ -18,23 +18,36 @@ from .general_utils.nerf_helpers import learning_rate_decay  # noqa: F401  (re-e
 class FlatBucket:
     """All parameters of one network as views into one contiguous fp32 buffer + Adam state."""
 
-    def __init__(self, module):
+    def __init__(self, module, storage=None):
+        """``storage``: (flat, grad, exp_avg, exp_avg_sq) slices of a larger allocation (`Trainer` places the buckets of
+        both DDNeRF networks in one arena so that a step has ONE memset, ONE all-reduce and ONE Adam launch); None: own
+        buffers."""
         self.module = module
         self.params = [p for p in module.parameters()]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        if storage is None:
+            self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+            self.grad = torch.zeros_like(self.flat)
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+        else:
+            self.flat, self.grad, self.exp_avg, self.exp_avg_sq = storage
+            for t in storage:
+                if t.numel() != total or t.device != dev or t.dtype != torch.float32:
+                    raise RuntimeError("ddnerf_b200: FlatBucket storage must be fp32 slices of the module's parameter count on its device")
         off = 0
         for p in self.params:
             n = p.numel()
             self.flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + n].view(p.shape)
             off += n
-        self.grad = torch.zeros_like(self.flat)
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step = 0
         self.sink = False
+
+    @staticmethod
+    def numel_of(module):
+        return sum(p.numel() for p in module.parameters())
 
     def install_sink(self):
         """bf16 mode: let the weight-gradient kernel accumulate directly into this bucket's flat gradient (views in the
@@ -171,9 +184,21 @@ class Trainer:
         self.model = model
         self.cfg = model.cfg
         self.is_dd = self.cfg.nerf.type == "DDNerfModel"
-        self.buckets = [FlatBucket(model.coarse)]
-        if self.is_dd:                                          # train_model.py:93-98 second optimizer
-            self.buckets.append(FlatBucket(model.fine))
+        # One arena {parameters, gradients, Adam moments} for all networks (train_model.py:86-98 keeps two optimizers over
+        # ~50 tensors): every bucket is a 256-byte-aligned slice of it, so a step zeroes, all-reduces and updates ONE buffer.
+        nets = [model.coarse] + ([model.fine] if self.is_dd else [])   # train_model.py:93-98 second optimizer
+        sizes = [FlatBucket.numel_of(m) for m in nets]
+        starts, total = [], 0
+        for n in sizes:
+            starts.append(total)
+            total += (n + 63) // 64 * 64
+        dev0 = next(model.coarse.parameters()).device
+        if all(p.device == dev0 for m in nets for p in m.parameters()):
+            self.arena = tuple(torch.zeros(total, device=dev0, dtype=torch.float32) for _ in range(4))
+            self.buckets = [FlatBucket(m, tuple(a[o:o + n] for a in self.arena)) for m, o, n in zip(nets, starts, sizes)]
+        else:
+            self.arena = None
+            self.buckets = [FlatBucket(m) for m in nets]
         if train_iters is None:
             try:
                 train_iters = int(self.cfg.experiment.train_iters)
@@ -195,6 +220,7 @@ class Trainer:
         # (all chunks forward, one backward), which needs the saved activations of the whole batch at once
         self.accumulate_chunks = True
         self._counter_iter = -1
+        self._consts = {}
         self._eager_calls = 0
         self._graph = None
         self._graph_tail = None
@@ -255,7 +281,11 @@ class Trainer:
         for b in self.buckets:
             if not b.sink:
                 b.install_sink()                                 # (no-op unless the network runs in bf16 mode)
-            b.begin_step()
+        if self.arena is not None and all(b.sink for b in self.buckets):
+            self.arena[1].zero_()                                # the gradient accumulators of all networks: one memset
+        else:
+            for b in self.buckets:
+                b.begin_step()
         coef = tp.loss_coeficients
         chunk = int(self.cfg.nerf.train.chunksize)
         ro, rd, rad = ray_origins.reshape(-1, 3), ray_directions.reshape(-1, 3), ray_rad.reshape(-1, 1)
@@ -271,11 +301,12 @@ class Trainer:
             mse_c, loss_c = mse3[:2], mse3[2]                    # (views: the kernel also wrote the weighted sum)
             tensors, grads = [out[0]["rgb"], out[1]["rgb"]], [g0, g1]
             if self.is_dd:                                       # train_model.py:163-167
-                dp = out[1]["dp_loss"].mean()
+                dp = out[1]["dp_loss"]
+                dp = dp.reshape(()) if dp.numel() == 1 else dp.mean()    # (.mean() of the [1] tensor: a view, no launch)
                 w_dp = tp.dp_coeficient / len(spans)
-                loss_c = loss_c + w_dp * dp.detach()
+                loss_c = torch.add(loss_c, dp.detach(), alpha=w_dp)
                 tensors.append(dp)
-                grads.append(torch.full_like(dp, w_dp))
+                grads.append(self._const(w_dp, dp.device))
             torch.autograd.backward(tensors, grads)
             del out, tensors, grads                              # the chunk's saved activations go back to the allocator
             loss = loss_c if loss is None else loss + loss_c
@@ -288,11 +319,43 @@ class Trainer:
             b.gather_grads()
         if hyper is not None and self.distributed and self.world > 1 and not collective_inside:
             return loss, mse                                     # two-graph mode: the collective and Adam follow outside
-        allreduce_gradients(self.buckets, self.world if self.distributed else 1)
+        self._allreduce()
         self._optimize(lr, hyper)
         return loss, mse
 
+    def _allreduce(self):
+        """The one collective of a data-parallel step: the gradient arena summed over ranks."""
+        world = self.world if self.distributed else 1
+        if world > 1 and self.arena is not None:
+            dist.all_reduce(self.arena[1], op=dist.ReduceOp.SUM)
+        else:
+            allreduce_gradients(self.buckets, world)
+
+    def _const(self, value, device):
+        """0-dim fp32 constant on the device, created once (a cotangent that is the same every iteration)."""
+        key = (float(value), str(device))
+        t = self._consts.get(key)
+        if t is None:
+            if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                return torch.full((), float(value), device=device, dtype=torch.float32)
+            t = self._consts[key] = torch.full((), float(value), device=device, dtype=torch.float32)
+        return t
+
     def _optimize(self, lr, hyper=None):
+        if self.arena is not None and len({b.step for b in self.buckets}) == 1:
+            # one Adam launch over the arena (the padding between buckets has zero gradients and stays zero)
+            for b in self.buckets:
+                b.check_alias()
+            flat, grad, m, v = self.arena
+            if hyper is None:
+                for b in self.buckets:
+                    b.step += 1
+                ops.adam_step(flat, grad, m, v, lr, self.buckets[0].step, grad_scale=1.0 / self.world)
+                for b in self.buckets:
+                    b.mark_dirty()
+            else:
+                ops.adam_step_dev(flat, grad, m, v, hyper)
+            return
         for b in self.buckets:
             if hyper is None:
                 b.adam(lr, grad_scale=1.0 / self.world)
@@ -320,7 +383,7 @@ class Trainer:
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
         if self._graph_tail is not None:                       # data parallel without graph-captured NCCL: eager all-reduce
-            allreduce_gradients(self.buckets, self.world)
+            self._allreduce()
             self._graph_tail.replay()
         for b in self.buckets:
             b.step += 1
@@ -392,7 +455,7 @@ class Trainer:
         self._static["loss"], self._static["mse"] = loss, mse
         self._graph_tail = None
         if self.distributed and self.world > 1 and not nccl_in_graph:   # the collective launched eagerly between two graphs
-            allreduce_gradients(self.buckets, self.world)
+            self._allreduce()
             torch.cuda.synchronize()
             tail = torch.cuda.CUDAGraph()
             with torch.cuda.graph(tail, pool=graph.pool()):

@@ -290,6 +290,22 @@ int ddnerf_dp_loss_backward(const float* t1, const float* t0, const float* w1, c
                             const float* pin0, int blender, const float* g_loss,
                             const float* scratch, float* g_w0, float* g_mus0, float* g_sigmas0,
                             int64_t N, int S0, int S1, void* stream);
+/* The loss term as DDNerfModel.predict forms it (models/models.py:287-289):
+ *   loss_out[0] = kl_div * scale + regs[2] + regs[3]
+ * with scale = the number of fine cells (t_vals.shape[1] - 1) and regs = {mus_loss, sig_loss, mus_reg, sig_reg} as
+ * ddnerf_composite_dd_forward wrote them.  Same kernels as ddnerf_dp_loss_forward (the finishing kernel adds the terms):
+ * replaces the reference's mul + two adds, and in the backward the slice / mul / add chain autograd builds for them. */
+int ddnerf_dp_loss_total_forward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                 const float* mus0, const float* sigmas0, const float* lt0,
+                                 const float* pin0, int blender, float scale, const float* regs,
+                                 float* loss_out, float* scratch, int64_t N, int S0, int S1, void* stream);
+/* g_loss: device pointer to the cotangent of loss_out[0].  Writes g_w0, g_mus0, g_sigmas0 [N,S0] (cotangent times scale
+ * through the KL term) and g_regs[4] = {0, 0, g, g}. */
+int ddnerf_dp_loss_total_backward(const float* t1, const float* t0, const float* w1, const float* w0,
+                                  const float* mus0, const float* sigmas0, const float* lt0,
+                                  const float* pin0, int blender, float scale, const float* g_loss,
+                                  const float* scratch, float* g_w0, float* g_mus0, float* g_sigmas0,
+                                  float* g_regs, int64_t N, int S0, int S1, void* stream);
 
 /* ---- training-step tail on the flat parameter bucket (train_model.py:156-177) ------------ */
 /* loss = sum_j coef_j * mse(rgb_j, target); writes g_rgb_j = coef_j*2*(rgb_j-target)/(3N).

@@ -146,3 +146,32 @@ def test_flat_bucket_detects_re_allocated_parameters():
     net.double()                                         # re-allocates every parameter (what module.to(other device) does)
     with pytest.raises(RuntimeError, match="no longer aliases"):
         b.check_alias()
+
+
+def test_draw_randoms_host_logic():
+    """GeneralMipNerfModel._draw_randoms: the four random tensors of one predict() (samplers.py:57,102/165,
+    volume_rendering_utils.py:31) come from one rand + one randn call as contiguous [N, n] tensors; injected tensors pass
+    through; modes that do not use a tensor get None (validation: perturb off)."""
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    cfg, _ = preset("config_blender", num_coarse=8, num_fine=12)
+    model = M.DDNerfModel(cfg)
+    N = 5
+    r = model._draw_randoms(N, "train", torch.device("cpu"))
+    assert r["t_rand"].shape == (N, 9) and r["u_rand"].shape == (N, 13)
+    assert r["noise0"].shape == (N, 8) and r["noise1"].shape == (N, 12)
+    assert all(v.is_contiguous() and v.dtype == torch.float32 for v in r.values())
+    assert 0.0 <= float(r["t_rand"].min()) and float(r["u_rand"].max()) < 1.0
+    # the two uniform tensors are the halves of one flat draw (same for the normal ones)
+    assert r["u_rand"].data_ptr() == r["t_rand"].data_ptr() + N * 9 * 4
+    assert r["noise1"].data_ptr() == r["noise0"].data_ptr() + N * 8 * 4
+    v = model._draw_randoms(N, "validation", torch.device("cpu"))
+    assert v["t_rand"] is None and v["u_rand"] is None                  # perturb = False
+    assert v["noise0"].shape == (N, 8)                                  # radiance_field_noise_std stays 1.0
+    inj = torch.full((N, 13), 0.25)
+    model.randoms = {"u_rand": inj}
+    r = model._draw_randoms(N, "train", torch.device("cpu"))
+    assert r["u_rand"].data_ptr() == inj.data_ptr() and r["t_rand"].shape == (N, 9)
+    cfg.nerf.train.radiance_field_noise_std = 0.0
+    r = model._draw_randoms(N, "train", torch.device("cpu"))
+    assert r["noise0"] is None and r["noise1"] is None

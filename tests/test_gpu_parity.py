@@ -643,6 +643,38 @@ def test_dp_loss_with_in_kernel_tails(ops, S0, S1):
         assert torch.nn.functional.cosine_similarity(g1.flatten().double(), g0.flatten().double(), dim=0).item() > 0.99999
 
 
+@pytest.mark.parametrize("S0,S1", [(16, 16), (32, 32), (128, 128), (300, 300)])
+def test_dp_loss_total_equals_reference_sequence(ops, S0, S1):
+    """ops.dp_loss_total == models.py:287-289 done with tensor ops on ops.dp_loss (kl * S1 + mus_reg + sig_reg, [1]):
+    forward bit-exact, cotangents of pdf_0 / mus_0 / sigmas_0 and of regs equal."""
+    N = 37
+    g, t0, w0, mus, sig, _, _ = _resample_inputs(N, S0, 90 + S0, peaked=False)
+    w0, sig = w0 + 0.05, sig + 0.15
+    t1 = torch.sort(torch.rand(N, S1 + 1, generator=g) * 3.8 + 2, dim=-1)[0]
+    t1[:, 0] = 2.0
+    w1 = torch.rand(N, S1, generator=g) + 0.05
+    regs0 = torch.tensor([0.7, 1.3, 0.021, 0.039])
+    res = []
+    for fused in (False, True):
+        a = [cu(x).clone().requires_grad_(True) for x in (w0, mus, sig, regs0)]
+        if fused:
+            total = ops.dp_loss_total(cu(t1), cu(t0), cu(w1), a[0], a[1], a[2], None, None, False, a[3], S1)
+        else:
+            kl = ops.dp_loss(cu(t1), cu(t0), cu(w1), a[0], a[1], a[2], None, None, False) * S1
+            total = (kl + a[3][2:3] + a[3][3:4])
+        assert total.shape == (1,)
+        (total.reshape(()) * 0.37).backward()
+        res.append((total.detach().cpu(), [x.grad.cpu() for x in a]))
+    if S0 <= 256:
+        assert torch.equal(res[0][0], res[1][0])
+    else:                                   # the generic kernels (S > 256) sum the per-ray values with atomics: order varies
+        close(res[1][0], res[0][0], 1e-6, 0.0)
+    for g1, g0 in zip(res[1][1][:3], res[0][1][:3]):
+        close(g1, g0, 2e-6, 1e-9)
+    assert torch.equal(res[1][1][3], torch.tensor([0.0, 0.0, 0.37, 0.37]))
+    assert torch.equal(res[0][1][3], res[1][1][3])
+
+
 # ---------------------------------------------------------------------------------------------
 # K5 depth-distribution loss
 # ---------------------------------------------------------------------------------------------
