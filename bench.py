@@ -410,6 +410,68 @@ def emit(line):
     _JSON_OUT.flush()
 
 
+def compositing_hbm(dev, n_rays_step, samples_step):
+    """BASELINE.json's third figure, `compositing HBM GB/s`: the alpha-compositing kernels (csrc/composite.cu: forward and
+    analytic backward of volume_render_radiance_field, volume_rendering_utils.py:6-84) timed alone, ALGORITHMIC bytes /
+    CUDA-event time, against the measured copy bandwidth.  Two shapes: the sweep's 65,536 rays x 128 samples (configs[4],
+    working set 235-370 MB > the 126 MB L2) and the benched step's own shape, where a launch moves 15-23 MB and runs for
+    about 10 us (launch floor; inside the step these kernels are nodes of the step's CUDA graph).  Each kernel is captured
+    into a one-node CUDA graph; an L2-sized buffer is rewritten between repetitions; median of 10."""
+    from ddnerf_b200 import _lib, ops
+    from ddnerf_b200.ops import _p, _stream
+    lib = _lib.load()
+    pk, pk_kind = peaks()
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)                 # 256 MB
+
+    def timed_kernel(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()                                               # noqa: F841 (outputs live with the graph)
+        g.replay()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            flush.add_(1.0)
+            a.record()
+            g.replay()
+            b.record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return ts[len(ts) // 2]
+
+    out = {"kernel": "composite_fwd_kernel / composite_bwd_kernel (csrc/composite.cu)", "unit": "GB/s", "peak": pk["hbm_gbs"],
+           "peak_kind": f"{pk_kind} copy bandwidth (MEASURED_PEAKS.json)",
+           "bytes": "algorithmic: forward 28 B/sample + 40 B/ray, backward 44 B/sample + 24 B/ray", "shapes": []}
+    for N, S in ((65536, 128), (n_rays_step, samples_step)):
+        gen = torch.Generator(device=dev).manual_seed(3)
+        raw = torch.randn(N, S, 4, device=dev, generator=gen)
+        noise = torch.randn(N, S, device=dev, generator=gen)
+        rd = torch.randn(N, 3, device=dev, generator=gen)
+        t = torch.sort(torch.rand(N, S + 1, device=dev, generator=gen) * 4 + 2, dim=-1)[0]
+        g_rgb, g_w = torch.randn(N, 3, device=dev, generator=gen), torch.randn(N, S, device=dev, generator=gen)
+        g_raw = torch.empty(N, S, 4, device=dev)
+
+        def fwd():
+            with torch.no_grad():
+                return ops.composite(raw, t, rd, noise, 1.0, None, False, True, False)
+
+        def bwd():
+            _lib.check(lib.ddnerf_composite_backward(_p(raw), 4, _p(t), _p(rd), rd.stride(0), _p(noise), 1.0, None, 0, 1,
+                                                     _p(g_rgb), None, None, _p(g_w), None, None, _p(g_raw), None, N, S,
+                                                     _stream()), "composite_backward")
+        R = N * S
+        b_f, b_b = R * 28 + N * 40, R * 44 + N * 24
+        ms_f, ms_b = timed_kernel(fwd), timed_kernel(bwd)
+        out["shapes"].append({"rays": N, "samples": S, "fwd_ms": ms_f, "fwd_gbs": b_f / ms_f / 1e6, "fwd_frac": b_f / ms_f / 1e6 / pk["hbm_gbs"],
+                              "bwd_ms": ms_b, "bwd_gbs": b_b / ms_b / 1e6, "bwd_frac": b_b / ms_b / 1e6 / pk["hbm_gbs"]})
+        del raw, noise, g_raw, g_w, t
+    out["achieved"] = out["shapes"][0]["fwd_gbs"]
+    out["frac"] = out["shapes"][0]["fwd_frac"]
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -425,6 +487,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-render", action="store_true", help="skip the full-frame render leg (configs[2])")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the compositing HBM GB/s block")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the DDNeRF 16,384 rays/GPU training block (configs[3])")
     ap.add_argument("--render-frames", type=int, default=5)
     ap.add_argument("--render-chunk", type=int, default=0, help="rays per chunk of the render leg (0: one chunk per rank)")
@@ -678,6 +741,8 @@ def main():
         line["train_cfg4"] = run_train_block(args, "cfg4", dev, world, rank, dist, K, W)
     if not args.no_render:
         line["render"] = run_render(args, dev, world, rank, dist)
+    if rank == 0 and world == 1 and not args.no_hbm_kernels:
+        line["compositing"] = compositing_hbm(dev, n_rays, cfg.nerf.train.num_coarse)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = min(args.cpu_rays, n_rays)
         rps, sec, threads = cpu_baseline(cfg, kind, n_cpu, 2, 1)

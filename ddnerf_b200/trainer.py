@@ -2,11 +2,12 @@
 data-parallel extension of SURVEY.md section 8e.
 
 The reference keeps 26 (+24) parameter tensors and steps two ``torch.optim.Adam`` objects over
-them tensor by tensor.  Here each network's parameters are views into ONE flat fp32 bucket; the
-gradients are gathered into a matching flat bucket, summed across ranks with a single NCCL
-all-reduce (rays shard across ranks, weights are replicated) and applied by one fused Adam kernel.
-The per-parameter ``nn.Parameter`` objects (names, shapes, ``state_dict``) stay what the
-reference's checkpoints expect.
+them tensor by tensor.  Here each network's parameters are views into a flat fp32 bucket, and the
+buckets of all networks (DDNeRF: coarse and fine) are slices of ONE arena with matching arenas for
+the gradients and the two Adam moments: a step zeroes the gradient arena once, sums it across ranks
+with a single NCCL all-reduce (rays shard across ranks, weights are replicated) and applies it with
+one fused Adam launch.  The per-parameter ``nn.Parameter`` objects (names, shapes, ``state_dict``)
+and the per-network optimizer states stay what the reference's checkpoints expect.
 """
 import torch
 import torch.distributed as dist
@@ -169,7 +170,7 @@ def allreduce_gradients(buckets, world):
 class Trainer:
     """Drives ``model.run_iter`` + loss + backward + (all-reduce) + Adam, one call per iteration.
 
-    ``use_graph=True`` captures the whole iteration (about 160 kernel launches and as many host-side
+    ``use_graph=True`` captures the whole iteration (20 kernel launches for mip-NeRF, 27 for DDNeRF, and many more host-side
     dispatches) into ONE CUDA graph after two eager iterations and replays it from then on; the values that
     change every iteration -- learning rate, Adam bias corrections, the annealed ``gaussian_smooth_factor`` --
     are computed ON THE DEVICE by the graph's first node from a device-resident iteration counter

@@ -296,3 +296,54 @@ def test_gradient_accumulation_over_ray_chunks(pname):
     assert torch.nn.functional.cosine_similarity(g0.double(), g1.double(), dim=0).item() > 0.9999999
     assert (w0 - w1).abs().max().item() < 1e-4
     assert mem1 < mem0                                                      # one chunk's saves instead of three
+
+
+def test_trainer_arena_holds_both_networks():
+    """Trainer places the flat buckets of both DDNeRF networks in ONE arena (parameters, gradients, Adam moments): the
+    buckets are 256-byte-aligned slices, the parameters alias them, a step zeroes / all-reduces / updates the arena as one
+    buffer and the padding between the buckets stays zero; differing Adam step counts fall back to per-bucket updates."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    from ddnerf_b200.trainer import Trainer
+    dev = torch.device(DEV)
+    N, s0, s1 = 128, 16, 16
+    cfg, _ = preset("config_blender", num_coarse=s0, num_fine=s1)
+    model = M.DDNerfModel(cfg)
+    model.coarse.load_state_dict(orc.init_mlp_params(True, seed=31))
+    model.fine.load_state_dict(orc.init_mlp_params(False, seed=32))
+    model.coarse.mlp_mode = model.fine.mlp_mode = "bf16"
+    model.to(dev)
+    tr = Trainer(model, train_iters=100, use_graph=False)
+    assert tr.arena is not None and len(tr.buckets) == 2
+    flat, grad, m, v = tr.arena
+    n0, n1 = tr.buckets[0].flat.numel(), tr.buckets[1].flat.numel()
+    off1 = (n0 + 63) // 64 * 64
+    assert flat.numel() == off1 + (n1 + 63) // 64 * 64
+    for b, off in zip(tr.buckets, (0, off1)):
+        for whole, part in zip(tr.arena, (b.flat, b.grad, b.exp_avg, b.exp_avg_sq)):
+            assert part.data_ptr() == whole.data_ptr() + 4 * off and part.data_ptr() % 256 == 0
+        b.check_alias()
+    w_before = flat.clone()
+    ro, rd, rad, _, _ = synth_rays("blender", N, seed=6)
+    target = torch.rand(N, 3, generator=torch.Generator().manual_seed(2))
+    args = [t.to(dev) for t in (ro, rd, rad, target)]
+    for _ in range(3):
+        tr.step(*args)
+    torch.cuda.synchronize()
+    assert [b.step for b in tr.buckets] == [3, 3]
+    pad = torch.ones(flat.numel(), dtype=torch.bool, device=dev)
+    pad[:n0] = False
+    pad[off1:off1 + n1] = False
+    for t in tr.arena:
+        assert t[pad].abs().max().item() == 0.0                     # zero gradients, zero moments, zero parameters
+    for b in tr.buckets:
+        assert b.grad.abs().max().item() > 0 and (b.flat - w_before[b.flat.data_ptr() // 4 - flat.data_ptr() // 4:][:b.flat.numel()]).abs().max().item() > 0
+    # a bucket restored from a checkpoint with another step count: the update falls back to one launch per bucket
+    tr.buckets[1].step = 7
+    tr.step(*args)
+    torch.cuda.synchronize()
+    assert [b.step for b in tr.buckets] == [4, 8]
+    for t in tr.arena:
+        assert t[pad].abs().max().item() == 0.0
