@@ -614,8 +614,8 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_forward(const float* raw, int raw_
                                         int white_background, int blender, float* rgb_map, float* disp, float* acc,
                                         float* weights, float* depth, float* cdisp, float* rgb, int64_t N, int S,
                                         void* stream) {
-    DDNERF_CHECK_ARG(raw && t && rd && rgb_map && disp && acc && weights && depth, "composite_forward: null pointer");
-    DDNERF_CHECK_ARG(!mus || cdisp, "composite_forward: mus given but cdisp is null");
+    DDNERF_CHECK_ARG(N == 0 || (raw && t && rd && rgb_map && disp && acc && weights && depth), "composite_forward: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || !mus || cdisp, "composite_forward: mus given but cdisp is null");
     DDNERF_CHECK_ARG(S >= 1 && S <= 512, "composite_forward: S=%d outside [1,512]", S);
     DDNERF_CHECK_ARG(raw_stride >= 4, "composite_forward: raw_stride=%d < 4", raw_stride);
     if (N == 0) return 0;
@@ -644,7 +644,7 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_backward(const float* raw, int raw
                                          const float* g_acc, const float* g_weights, const float* g_depth,
                                          const float* g_cdisp, float* g_raw, float* g_mus, int64_t N, int S,
                                          void* stream) {
-    DDNERF_CHECK_ARG(raw && t && rd && g_raw, "composite_backward: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (raw && t && rd && g_raw), "composite_backward: null pointer");
     DDNERF_CHECK_ARG(S >= 1 && S <= 512, "composite_backward: S=%d outside [1,512]", S);
     DDNERF_CHECK_ARG(reinterpret_cast<uintptr_t>(g_raw) % 16 == 0, "composite_backward: g_raw not 16-byte aligned");
     if (N == 0) return 0;
@@ -675,7 +675,7 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_dd_forward(const float* raw6, cons
                                            float dist_reg_coef, float* rgb_map, float* disp, float* acc, float* weights,
                                            float* depth, float* cdisp, float* mus, float* sigmas, float* regs,
                                            float* scratch, int64_t N, int S, void* stream) {
-    DDNERF_CHECK_ARG(raw6 && t && rd && rgb_map && disp && acc && weights && depth && cdisp && mus && sigmas && regs && scratch,
+    DDNERF_CHECK_ARG(regs && (N == 0 || (raw6 && t && rd && rgb_map && disp && acc && weights && depth && cdisp && mus && sigmas && scratch)),
                      "composite_dd_forward: null pointer");
     DDNERF_CHECK_ARG(S >= 1 && S <= 512, "composite_dd_forward: S=%d outside [1,512]", S);
     DDNERF_CHECK_ARG(reinterpret_cast<uintptr_t>(raw6) % 8 == 0, "composite_dd_forward: raw6 not 8-byte aligned");
@@ -705,7 +705,7 @@ extern "C" DDNERF_EXPORT int ddnerf_composite_dd_backward(const float* raw6, con
                                             const float* g_acc, const float* g_weights, const float* g_depth,
                                             const float* g_cdisp, const float* g_mus, const float* g_sigmas,
                                             const float* g_regs, float* g_raw6, int64_t N, int S, void* stream) {
-    DDNERF_CHECK_ARG(raw6 && t && rd && g_raw6, "composite_dd_backward: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (raw6 && t && rd && g_raw6), "composite_dd_backward: null pointer");
     DDNERF_CHECK_ARG(S >= 1 && S <= 512, "composite_dd_backward: S=%d outside [1,512]", S);
     DDNERF_CHECK_ARG(reinterpret_cast<uintptr_t>(raw6) % 8 == 0 && reinterpret_cast<uintptr_t>(g_raw6) % 8 == 0,
                      "composite_dd_backward: raw6 / g_raw6 not 8-byte aligned");

@@ -590,7 +590,7 @@ using namespace ddnerf;
 static int dp_loss_forward_impl(const float* t1, const float* t0, const float* w1, const float* w0, const float* mus0,
                                 const float* sigmas0, const float* lt0, const float* pin0, int blender, DpTotal tt,
                                 float* loss_out, float* scratch, int64_t N, int S0, int S1, void* stream) {
-    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && loss_out && scratch, "dp_loss_forward: null pointer");
+    DDNERF_CHECK_ARG(loss_out && scratch && (N == 0 || (t1 && t0 && w1 && w0 && mus0 && sigmas0)), "dp_loss_forward: null pointer");
     DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_forward: lt0 and pin0 go together (both NULL: computed in the kernel)");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_forward: S0=%d S1=%d unsupported", S0, S1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -629,7 +629,7 @@ static int dp_loss_backward_impl(const float* t1, const float* t0, const float* 
                                  const float* sigmas0, const float* lt0, const float* pin0, int blender, DpTotal tt,
                                  const float* g_loss, const float* scratch, float* g_w0, float* g_mus0, float* g_sigmas0,
                                  int64_t N, int S0, int S1, void* stream) {
-    DDNERF_CHECK_ARG(t1 && t0 && w1 && w0 && mus0 && sigmas0 && g_loss && scratch && g_w0 && g_mus0 && g_sigmas0,
+    DDNERF_CHECK_ARG(g_loss && scratch && (N == 0 || (t1 && t0 && w1 && w0 && mus0 && sigmas0 && g_w0 && g_mus0 && g_sigmas0)),
                      "dp_loss_backward: null pointer");
     DDNERF_CHECK_ARG((lt0 == nullptr) == (pin0 == nullptr), "dp_loss_backward: lt0 and pin0 go together");
     DDNERF_CHECK_ARG(S0 >= 1 && S1 >= 1 && S0 <= 1024 && S1 <= 1024, "dp_loss_backward: S0=%d S1=%d unsupported", S0, S1);

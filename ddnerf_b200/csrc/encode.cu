@@ -61,7 +61,7 @@ using namespace ddnerf;
 
 extern "C" DDNERF_EXPORT int ddnerf_pack_rays(const float* ray_origins, const float* ray_directions, const float* ray_radii,
                                               float near, float far, int64_t N, float* rays, void* stream) {
-    DDNERF_CHECK_ARG(ray_origins && ray_directions && ray_radii && rays, "pack_rays: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (ray_origins && ray_directions && ray_radii && rays), "pack_rays: null pointer");
     DDNERF_CHECK_ARG((reinterpret_cast<uintptr_t>(rays) & 15u) == 0, "pack_rays: rays must be 16-byte aligned");
     if (N == 0) return 0;
     pack_rays_kernel<<<ceil_div(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ray_origins, ray_directions, ray_radii, near, far,
@@ -72,7 +72,7 @@ extern "C" DDNERF_EXPORT int ddnerf_pack_rays(const float* ray_origins, const fl
 
 extern "C" DDNERF_EXPORT int ddnerf_encode(const float* rays, const float* t_vals, float* enc_out, int64_t ld_enc, float* dir_out,
                              int64_t ld_dir, int64_t N, int S, int ray_shape, void* stream) {
-    DDNERF_CHECK_ARG(rays && t_vals && enc_out, "encode: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || S == 0 || (rays && t_vals && enc_out), "encode: null pointer");
     DDNERF_CHECK_ARG(ray_shape == 0 || ray_shape == 1, "encode: ray_shape=%d (0 cone, 1 cylinder)", ray_shape);
     DDNERF_CHECK_ARG(ld_enc >= 96 && (!dir_out || ld_dir >= 27), "encode: leading dimension too small");
     if (N == 0 || S == 0) return 0;

@@ -585,7 +585,7 @@ using namespace ddnerf;
 
 extern "C" DDNERF_EXPORT int ddnerf_sample_first_cycle(const float* near, const float* far, int64_t ray_stride, const float* t_rand,
                                          float* t_out, int64_t N, int S, int lindisp, void* stream) {
-    DDNERF_CHECK_ARG(near && far && t_out, "sample_first_cycle: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (near && far && t_out), "sample_first_cycle: null pointer");
     DDNERF_CHECK_ARG(S >= 1, "sample_first_cycle: S=%d < 1", S);
     if (N == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -604,7 +604,7 @@ static int warps_per_block(int per_warp_floats) {
 
 extern "C" DDNERF_EXPORT int ddnerf_sample_pdf(const float* bins, const float* weights, const float* rand, float* out,
                                  int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, void* stream) {
-    DDNERF_CHECK_ARG(bins && weights && out, "sample_pdf: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (bins && weights && out), "sample_pdf: null pointer");
     DDNERF_CHECK_ARG(S >= 1 && S <= 2048 && n >= 2, "sample_pdf: S=%d n=%d unsupported", S, n);
     if (N == 0) return 0;
     double s = 1.0 / n;
@@ -647,7 +647,12 @@ static int sample_dd_impl(const float* bins, const float* weights, const float* 
         int np2 = next_pow2(n);
         int per_warp = (S + 2) + S + (S + 1) + (S + 1) + np2;
         int wpb = warps_per_block(per_warp);
-        DDNERF_CHECK_ARG(wpb >= 1, "sample_pdf_mu_sigma: S=%d n=%d needs too much shared memory", S, n);
+        if (wpb < 1) {                      // the largest shapes (S = 2048, n up to 4096: 49 KB per ray) pass the 48 KB default
+            wpb = 1;
+            const size_t bytes = (size_t)per_warp * sizeof(float);
+            DDNERF_CHECK_ARG(bytes <= 200 * 1024, "sample_pdf_mu_sigma: S=%d n=%d needs too much shared memory", S, n);
+            cudaFuncSetAttribute(sample_pdf_mu_sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        }
         sample_pdf_mu_sigma_kernel<<<ceil_div(N, wpb), wpb * 32, (size_t)wpb * per_warp * sizeof(float), st>>>(
             bins, weights, mus, sigmas, part_inside, left_tail, rand, out, idx_out, N, S, n, np2, pdf_padding, near_cfg,
             far_cfg, us, per_warp, smooth);
@@ -660,7 +665,7 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma(const float* bins, const
                                           const float* part_inside, const float* left_tail, const float* rand, float* out,
                                           int32_t* idx_out, int64_t N, int S, int n, int pdf_padding, float near_cfg,
                                           float far_cfg, void* stream) {
-    DDNERF_CHECK_ARG(bins && weights && mus && sigmas && part_inside && left_tail && out,
+    DDNERF_CHECK_ARG(N == 0 || (bins && weights && mus && sigmas && part_inside && left_tail && out),
                      "sample_pdf_mu_sigma: null pointer");
     return sample_dd_impl(bins, weights, mus, sigmas, part_inside, left_tail, Smooth{1.0f, nullptr}, rand, out, idx_out, N, S,
                           n, pdf_padding, near_cfg, far_cfg, stream);
@@ -670,7 +675,7 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma_fused(const float* bins,
                                                 const float* sigmas, float smooth, const float* smooth_dev,
                                                 const float* rand, float* out, int32_t* idx_out, int64_t N, int S, int n,
                                                 int pdf_padding, float near_cfg, float far_cfg, void* stream) {
-    DDNERF_CHECK_ARG(bins && weights && mus && sigmas && out, "sample_pdf_mu_sigma_fused: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || (bins && weights && mus && sigmas && out), "sample_pdf_mu_sigma_fused: null pointer");
     DDNERF_CHECK_ARG(smooth_dev || smooth > 0.f, "sample_pdf_mu_sigma_fused: gaussian_smooth_factor=%g must be positive", smooth);
     return sample_dd_impl(bins, weights, mus, sigmas, nullptr, nullptr, Smooth{smooth, smooth_dev}, rand, out, idx_out, N, S, n,
                           pdf_padding, near_cfg, far_cfg, stream);
@@ -678,7 +683,7 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_pdf_mu_sigma_fused(const float* bins,
 
 extern "C" DDNERF_EXPORT int ddnerf_find_interval(const float* cdf, const float* u, int32_t* idx_out, int64_t N, int S, int n,
                                     void* stream) {
-    DDNERF_CHECK_ARG(cdf && u && idx_out, "find_interval: null pointer");
+    DDNERF_CHECK_ARG(N == 0 || n == 0 || (cdf && u && idx_out), "find_interval: null pointer");
     if (N == 0 || n == 0) return 0;
     find_interval_kernel<<<ceil_div(N * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cdf, u, idx_out, N, S, n);
     DDNERF_LAUNCHED("find_interval", 1);

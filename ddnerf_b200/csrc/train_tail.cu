@@ -130,7 +130,7 @@ extern "C" DDNERF_EXPORT int ddnerf_train_schedule(int64_t* state, float* hyper,
 
 extern "C" DDNERF_EXPORT int ddnerf_mse_loss(const float* rgb0, const float* rgb1, const float* target, float coef0, float coef1,
                                float* g_rgb0, float* g_rgb1, float* mse_out, int64_t N, void* stream) {
-    DDNERF_CHECK_ARG(rgb0 && target && mse_out, "mse_loss: null pointer");
+    DDNERF_CHECK_ARG(mse_out && (N == 0 || (rgb0 && target)), "mse_loss: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(mse_out, 0, 3 * sizeof(float), st);
     if (N == 0) return 0;

@@ -10,7 +10,9 @@
  *     here); outputs are pre-sized by the caller; fp32 row-major unless stated;
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync;
  *   - return value 0 = ok, non-zero = error, message via ddnerf_last_error() (thread-local);
- *   - N = rays, S = samples (intervals) of the current pass, fence-posts t[N, S+1].
+ *   - N = rays, S = samples (intervals) of the current pass, fence-posts t[N, S+1];
+ *   - N == 0 (an empty chunk or shard) is valid for every per-ray entry point: the per-ray pointers may then be NULL,
+ *     no kernel is launched, scalar outputs (losses, regs) are written as for an empty sum.
  */
 #ifndef DDNERF_B200_H_
 #define DDNERF_B200_H_

@@ -866,3 +866,72 @@ def test_pack_rays_vs_reference_expression(N):
     assert out.shape == (N, 12)
     assert torch.equal(out[:, :9], ref[:, :9])
     assert (out[:, 9:] - ref[:, 9:]).abs().max().item() <= 1.2e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the boundary: empty ray batches, the largest sizes the entry points accept
+# ---------------------------------------------------------------------------------------------
+def test_zero_rays_every_operator(ops):
+    """N = 0 rays (the last, empty chunk of a sharded frame; a rank with no rows): every operator returns correctly shaped
+    empty tensors without launching a kernel (a grid of 0 blocks is a launch error), the scalar losses are 0, and autograd
+    through them works."""
+    S, n = 8, 9
+    z = lambda *shape: torch.zeros(*shape, device=DEV)
+    assert ops.sample_first_cycle(z(0, 1), z(0, 1), S, False, z(0, S + 1)).shape == (0, S + 1)
+    assert ops.sample_pdf(z(0, S + 1), z(0, S), n, True, z(0, n)).shape == (0, n)
+    assert ops.sample_pdf_mu_sigma(z(0, S + 1), z(0, S), z(0, S), z(0, S), z(0, S), z(0, S), n, True, 2.0, 6.0, z(0, n)).shape == (0, n)
+    assert ops.sample_pdf_mu_sigma_fused(z(0, S + 1), z(0, S), z(0, S), z(0, S), 1.4, n, True, 2.0, 6.0, z(0, n)).shape == (0, n)
+    assert ops.find_interval(z(0, S + 1), z(0, n)).shape == (0, n)
+    assert ops.pack_rays(z(0, 3), z(0, 3), z(0, 1), 2.0, 6.0).shape == (0, 12)
+    assert ops.encode(z(0, 12), z(0, S + 1)).shape == (0, 123)
+    raw = z(0, S, 4).requires_grad_(True)
+    out = ops.composite(raw, z(0, S + 1), z(0, 3), z(0, S), 1.0, None, False, True, True)
+    assert out[0].shape == (0, 3) and out[3].shape == (0, S) and out[6].shape == (0, S, 3)
+    (out[0].sum() + out[3].sum()).backward()
+    assert raw.grad.shape == (0, S, 4)
+    raw6 = z(0, S, 6).requires_grad_(True)
+    dd = ops.composite_dd(raw6, z(0, S + 1), z(0, 3), z(0, S), 1.0, False, True, 0.03)
+    assert dd[3].shape == (0, S) and dd[6].shape == (0, S) and dd[8].shape == (4,)
+    assert dd[8].abs().max().item() == 0.0
+    w0, mu, sg = (z(0, S).requires_grad_(True) for _ in range(3))
+    kl = ops.dp_loss(z(0, n), z(0, S + 1), z(0, S), w0, mu, sg, None, None, True)
+    assert kl.item() == 0.0
+    regs = torch.tensor([0.5, 0.25, 0.0625, 0.125], device=DEV, requires_grad=True)
+    tot = ops.dp_loss_total(z(0, n), z(0, S + 1), z(0, S), w0, mu, sg, None, None, True, regs, S)
+    assert tot.shape == (1,) and tot.item() == 0.0625 + 0.125
+    tot.sum().backward()
+    assert w0.grad.shape == (0, S) and torch.equal(regs.grad.cpu(), torch.tensor([0.0, 0.0, 1.0, 1.0]))
+    torch.cuda.synchronize()
+
+
+def test_maximum_sizes_vs_oracle(ops):
+    """The largest shapes the entry points accept (include/ddnerf_b200.h): resamplers at S = 2048 cells / 2049 samples,
+    compositor at S = 512, dp-loss at 1024 x 1024 -- the generic kernels behind the lane-group fast paths."""
+    N = 3
+    g, bins, w, mus, sig, lt, pin = _resample_inputs(N, 2048, 5, peaked=True)
+    sig = sig + 0.05
+    lt = orc.normal_cdf((0 - mus) / sig)
+    pin = orc.normal_cdf((1 - mus) / sig) - lt
+    for det in (True, False):
+        rand = None if det else torch.rand(N, 2049, generator=g)
+        s_ref, _ = orc.sample_pdf(bins, w, 2049, True, rand)
+        close(ops.sample_pdf(cu(bins), cu(w), 2049, True, cu(rand)), s_ref, 1e-5, 2e-5)
+        d_ref, _ = orc.sample_pdf_with_mu_sigma(bins, w, mus, sig, pin, lt, 2049, True, 2.0, 6.0, rand)
+        d = ops.sample_pdf_mu_sigma(cu(bins), cu(w), cu(mus), cu(sig), cu(pin), cu(lt), 2049, True, 2.0, 6.0, cu(rand))
+        assert (d[:, 1:] >= d[:, :-1]).all()
+        err = (d.cpu() - d_ref).abs()
+        assert (err > 3e-4 + 1e-4 * d_ref.abs()).float().mean().item() < 2e-3 and err.max().item() < 5e-2
+    with pytest.raises(RuntimeError):
+        ops.sample_pdf(cu(torch.zeros(1, 2050)), cu(torch.ones(1, 2049)), 9, True, None)          # S = 2049 is refused
+    with pytest.raises(RuntimeError):
+        ops.composite(cu(torch.zeros(1, 513, 4)), cu(torch.zeros(1, 514)), cu(torch.ones(1, 3)), None, 0.0, None, False, True, False)
+    # dp-loss, 1024 coarse x 1024 fine cells
+    g, t0, w0, mus, sig, _, _ = _resample_inputs(N, 1024, 6, peaked=False)
+    w0, sig = w0 + 0.05, sig + 0.15
+    lt = orc.normal_cdf((0 - mus) / sig)
+    pin = orc.normal_cdf((1 - mus) / sig) - lt
+    t1 = torch.sort(torch.rand(N, 1025, generator=g) * 3.8 + 2, dim=-1)[0]
+    t1[:, 0] = 2.0
+    w1 = torch.rand(N, 1024, generator=g) + 0.05
+    ref = orc.estimate_dp_loss(t1, t0, w1, w0, mus, sig, lt, pin, False)
+    close(ops.dp_loss(cu(t1), cu(t0), cu(w1), cu(w0), cu(mus), cu(sig), cu(lt), cu(pin), False), ref, 5e-4, 1e-6)
