@@ -11,6 +11,10 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph --no-render --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
 python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.md
+# the DDNeRF step (cfg1: config_blender.yml, 1024 rays)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches_cfg1.csv \
+    python bench.py --workload cfg1 --steps 2 --warmup 3 --no-graph --no-render --no-cfg4 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches_cfg1.log 2>&1
+python tools/summarize_launches.py gpurun_out/${TAG}_launches_cfg1.csv > gpurun_out/${TAG}_launches_cfg1_summary.md
 # full captures of the MLP kernels (micro-benchmark, 4096 rays x 128 samples)
 cap() {  # name regex skip extra-args
   ncu --set full --clock-control none --import-source on -k "regex:$2" -c 1 -s $3 -f -o /tmp/ncu_$TAG/$1 \
