@@ -935,3 +935,46 @@ def test_maximum_sizes_vs_oracle(ops):
     w1 = torch.rand(N, 1024, generator=g) + 0.05
     ref = orc.estimate_dp_loss(t1, t0, w1, w0, mus, sig, lt, pin, False)
     close(ops.dp_loss(cu(t1), cu(t0), cu(w1), cu(w0), cu(mus), cu(sig), cu(lt), cu(pin), False), ref, 5e-4, 1e-6)
+
+
+@pytest.mark.parametrize("pname", ["config_blender", "config_blender_mipnerf"])
+def test_run_iter_ragged_chunks_equal_one_chunk(ops, pname):
+    """models.py:40-73: run_iter walks the rays in chunks of cfg.nerf[mode].chunksize and concatenates the per-chunk dicts.
+    A 5 x 7 validation frame in chunks of 16, 16 and 3 rays equals the same frame in one chunk (rays are independent), the
+    image shapes are restored, and in train mode the per-chunk scalars come back as [n_chunks] vectors (the caller takes
+    the mean, train_model.py:165)."""
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    H, W, S = 5, 7, 16
+    N = H * W
+    ro, rd, rad, _, _ = synth_rays("blender", N, seed=12)
+    g = torch.Generator().manual_seed(4)
+    rnd = dict(t_rand=torch.rand(N, S + 1, generator=g), noise0=torch.randn(N, S, generator=g),
+               u_rand=torch.rand(N, S + 1, generator=g), noise1=torch.randn(N, S, generator=g))
+    outs = []
+    for chunk in (16, 4096):
+        cfg, _ = preset(pname, num_coarse=S, num_fine=S, chunksize=chunk)
+        is_dd = cfg.nerf.type == "DDNerfModel"
+        model = getattr(M, cfg.nerf.type)(cfg)
+        model.coarse.load_state_dict(orc.init_mlp_params(is_dd, seed=41))
+        if is_dd:
+            model.fine.load_state_dict(orc.init_mlp_params(False, seed=42))
+        model.to(torch.device(DEV))
+        model.randoms = {k: cu(v) for k, v in rnd.items()}
+        model.eval()
+        with torch.no_grad():
+            val = model.run_iter(cu(ro).view(H, W, 3), cu(rd).view(H, W, 3), cu(rad).view(H, W, 1), mode="validation")
+        model.train()
+        trn = model.run_iter(cu(ro), cu(rd), cu(rad), mode="train", rgb_target=cu(torch.rand(N, 3, generator=g)))
+        outs.append((val, trn, is_dd))
+    (va, ta, is_dd), (vb, tb, _) = outs
+    for j in range(2):
+        assert va[j]["rgb"].shape == (H, W, 3) and va[j]["depth"].shape == (H, W) and va[j]["weights"].shape == (N, S)
+        for k in ("rgb", "disp", "acc", "depth", "weights"):
+            close(va[j][k], vb[j][k], 1e-6, 1e-6)
+            close(ta[j][k], tb[j][k], 1e-6, 1e-6)
+    if is_dd:
+        assert ta[1]["dp_loss"].shape == (3,) and tb[1]["dp_loss"].shape == (1,)
+        assert ta[0]["mus_reg"].shape == (3,) and ta[0]["sig_loss"].shape == (3,)
+        assert torch.isfinite(ta[1]["dp_loss"]).all()
