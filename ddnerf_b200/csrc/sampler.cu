@@ -23,67 +23,82 @@ __device__ __forceinline__ float linspace01(int idx, int steps, float step) {   
     return idx < steps / 2 ? step * (float)idx : 1.0f - step * (float)(steps - idx - 1);
 }
 
-// One warp per ray, lanes stride over the S+1 fence-posts (coalesced, no integer division).  The jitter
-// needs the neighbouring fence-posts: they come from the adjacent lanes by shuffle; the two lanes at the
-// chunk edges take them from the previous chunk's last / the next chunk's first value.  All of a ray's
-// random numbers are requested before the first is used (K chunks, compile time), otherwise the kernel is
-// bound by one DRAM latency per chunk.
-// R rays per warp: the only way to keep enough bytes in flight -- one ray's (S+1) * 4 bytes per warp leave the
-// memory system idle most of the time.
-template <int K, int R>
-__global__ void __launch_bounds__(256) first_cycle_kernel(const float* __restrict__ near, const float* __restrict__ far,
-                                                           int64_t ray_stride, const float* __restrict__ t_rand,
-                                                           float* __restrict__ out, int64_t N, int S, int lindisp) {
-    const int lane = threadIdx.x & 31;
-    const int64_t ray0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
-    if (ray0 >= N) return;
-    const int steps = S + 1;
-    float rnd[R][K], nrv[R], frv[R];
+// Element-parallel over the FLAT [N, S+1] array: a thread owns four or eight consecutive fence-posts (16-byte loads of the
+// random numbers, all in flight before the first use; 16-byte stores), finds its ray with one multiply-shift division
+// (Granlund-Montgomery: the divisor S+1 is a launch constant) and carries the three neighbouring linspace values along the
+// row, re-seeding them when its elements cross into the next ray.  ~35 instructions per fence-post; the round-1 kernel
+// (one warp per four rays, neighbours by shuffle) spent ~150: its 32-lane chunks left 20 % of the lanes idle at
+// S+1 = 2^m + 1 and its rows of 4 (S+1) bytes were never sector-aligned.  Same arithmetic, same rounding.
+struct FastDiv { uint32_t magic; int sh1, sh2; };
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& d) {
+    const uint32_t t = __umulhi(d.magic, n);
+    return (t + ((n - t) >> d.sh1)) >> d.sh2;
+}
+
+template <bool LINDISP, int V>
+__global__ void __launch_bounds__(256) first_cycle_flat_kernel(const float* __restrict__ near, const float* __restrict__ far,
+                                                                int64_t ray_stride, const float* __restrict__ t_rand,
+                                                                float* __restrict__ out, uint32_t total, int S,
+                                                                float step, FastDiv dv, int vec_ok) {
+    constexpr bool lindisp = LINDISP;
+    // V fence-posts per thread: 8 (two 16-byte loads in flight per thread) from 4 M elements up, 4 below (more threads)
+    const uint32_t e0 = (blockIdx.x * 256u + threadIdx.x) * (uint32_t)V;
+    if (e0 >= total) return;
+    const uint32_t steps = (uint32_t)S + 1u;
+    const bool full = e0 + (uint32_t)(V - 1) < total;
+    float rnd[V];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int64_t ray = min(ray0 + r, N - 1);
-        const float* rr = t_rand ? t_rand + ray * steps : nullptr;
+    for (int j = 0; j < V; ++j) rnd[j] = 0.f;
+    if (t_rand) {
+        if (vec_ok && full) {
 #pragma unroll
-        for (int c = 0; c < K; ++c) rnd[r][c] = (rr && c * 32 + lane <= S) ? __ldg(rr + c * 32 + lane) : 0.f;
-        nrv[r] = __ldg(near + ray * ray_stride); frv[r] = __ldg(far + ray * ray_stride);
-    }
-    const float step = 1.0f / (float)S;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (ray0 + r >= N) break;
-        const float nr = nrv[r], fr = frv[r];
-        const float inr = lindisp ? 1.0f / nr : 0.f, ifr = lindisp ? 1.0f / fr : 0.f;
-        auto tv = [&](int k) {
-            k = min(max(k, 0), S);
-            float s = linspace01(k, steps, step);
-            return lindisp ? 1.0f / (inr * (1.0f - s) + ifr * s) : nr * (1.0f - s) + fr * s;
-        };
-        float* orow = out + (ray0 + r) * steps;
-        float cur = tv(lane), prev_last = cur;          // prev_last: value at index (chunk start - 1)
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-            const int i = c * 32 + lane;
-            if (c * 32 > S) break;
-            const float nxt_chunk = tv(i + 32);         // next chunk's values (clamped index)
-            float lo_n = __shfl_up_sync(FULL, cur, 1);  // t[i-1]
-            float hi_n = __shfl_down_sync(FULL, cur, 1);// t[i+1]
-            const float next_first = __shfl_sync(FULL, nxt_chunk, 0);
-            if (lane == 0) lo_n = prev_last;
-            if (lane == 31) hi_n = next_first;
-            prev_last = __shfl_sync(FULL, cur, 31);
-            if (i <= S) {
-                float t = cur;
-                if (t_rand) {                           // samplers.py:52-60
-                    float lower = i == 0 ? cur : 0.5f * (cur + lo_n);
-                    float upper = i == S ? cur : 0.5f * (hi_n + cur);
-                    t = lower + (upper - lower) * rnd[r][c];
-                    if (i == 0) t = nr;
-                    if (i == S) t = fr;
-                }
-                orow[i] = t;
+            for (int q = 0; q < V / 4; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(t_rand + e0) + q);
+                rnd[4 * q] = v.x; rnd[4 * q + 1] = v.y; rnd[4 * q + 2] = v.z; rnd[4 * q + 3] = v.w;
             }
-            cur = nxt_chunk;
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) if (e0 + j < total) rnd[j] = __ldg(t_rand + e0 + j);
         }
+    }
+    uint32_t ray = fast_div(e0, dv);
+    int i = (int)(e0 - ray * steps);
+    float nr, fr, inr, ifr;
+    auto load_ray = [&](uint32_t r) {
+        nr = __ldg(near + (int64_t)r * ray_stride); fr = __ldg(far + (int64_t)r * ray_stride);
+        inr = lindisp ? 1.0f / nr : 0.f; ifr = lindisp ? 1.0f / fr : 0.f;
+    };
+    auto tv = [&](int k) {                               // samplers.py:32-41 at fence-post k (clamped: edge values are unused)
+        k = min(max(k, 0), S);
+        const float sfrac = linspace01(k, (int)steps, step);
+        return lindisp ? 1.0f / (inr * (1.0f - sfrac) + ifr * sfrac) : nr * (1.0f - sfrac) + fr * sfrac;
+    };
+    load_ray(ray);
+    float prev = tv(i - 1), cur = tv(i), nxt = tv(i + 1);
+    float res[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        float t = cur;
+        if (t_rand) {                                    // samplers.py:52-60
+            const float lower = i == 0 ? cur : 0.5f * (cur + prev);
+            const float upper = i == S ? cur : 0.5f * (nxt + cur);
+            t = lower + (upper - lower) * rnd[j];
+            if (i == 0) t = nr;
+            if (i == S) t = fr;
+        }
+        res[j] = t;
+        if (j < V - 1) {
+            if (i < S) { ++i; prev = cur; cur = nxt; nxt = tv(i + 1); }
+            else if (e0 + j + 1 < total) { ++ray; i = 0; load_ray(ray); prev = cur = tv(0); nxt = tv(1); }
+        }
+    }
+    if (vec_ok && full) {
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q)
+            reinterpret_cast<float4*>(out + e0)[q] = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) if (e0 + j < total) out[e0 + j] = res[j];
     }
 }
 
@@ -589,9 +604,24 @@ extern "C" DDNERF_EXPORT int ddnerf_sample_first_cycle(const float* near, const 
     DDNERF_CHECK_ARG(S >= 1, "sample_first_cycle: S=%d < 1", S);
     if (N == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (S + 1 <= 32 * 2) first_cycle_kernel<2, 8><<<ceil_div(N, 8 * 8), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
-    else if (S + 1 <= 32 * 5) first_cycle_kernel<5, 4><<<ceil_div(N, 8 * 4), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
-    else if (S + 1 <= 32 * 9) first_cycle_kernel<9, 2><<<ceil_div(N, 8 * 2), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
+    const int64_t total = N * (int64_t)(S + 1);
+    if (total < (int64_t)0xffff0000u && S < 65536) {
+        const uint32_t d = (uint32_t)S + 1u;             // multiply-shift division by S+1 (exact for every 32-bit dividend)
+        int l = 0;
+        while ((1ull << l) < d) ++l;
+        FastDiv dv{(uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1ull), l < 1 ? l : 1, l > 1 ? l - 1 : 0};
+        const int vec_ok = (reinterpret_cast<uintptr_t>(t_out) % 32 == 0) && (!t_rand || reinterpret_cast<uintptr_t>(t_rand) % 32 == 0);
+        const float step = 1.0f / (float)S;
+        auto launch = [&](auto lin, auto vv) {
+            constexpr bool L = decltype(lin)::value;
+            constexpr int V = decltype(vv)::value;
+            first_cycle_flat_kernel<L, V><<<ceil_div(ceil_div(total, V), 256), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out,
+                                                                                          (uint32_t)total, S, step, dv, vec_ok);
+        };
+        const bool big = total >= (1 << 22);
+        if (lindisp) { if (big) launch(std::true_type{}, std::integral_constant<int, 8>{}); else launch(std::true_type{}, std::integral_constant<int, 4>{}); }
+        else { if (big) launch(std::false_type{}, std::integral_constant<int, 8>{}); else launch(std::false_type{}, std::integral_constant<int, 4>{}); }
+    }
     else first_cycle_generic_kernel<<<ceil_div(N * (S + 1), 256), 256, 0, st>>>(near, far, ray_stride, t_rand, t_out, N, S, lindisp);
     DDNERF_LAUNCHED("sample_first_cycle", 1);
     return 0;

@@ -240,6 +240,26 @@ def test_first_cycle_shapes_vs_oracle(ops, S):
         close(ops.sample_first_cycle(cu(near), cu(far), S, lind), orc.sample_first_cycle(near, far, S, lind), 1e-6, 1e-6)
 
 
+def test_first_cycle_large_and_unaligned(ops):
+    """The flat kernel's eight-per-thread variant (>= 4 M fence-posts), per-ray near / far, and buffers that are not 32-byte
+    aligned (scalar loads / stores instead of 16-byte ones)."""
+    N, S = 33000, 128
+    g = torch.Generator().manual_seed(77)
+    near, far = torch.rand(N, 1, generator=g) + 1.5, torch.rand(N, 1, generator=g) + 5.0
+    rnd = torch.rand(N, S + 1, generator=g)
+    ref = orc.sample_first_cycle(near, far, S, False, rnd)
+    close(ops.sample_first_cycle(cu(near), cu(far), S, False, cu(rnd)), ref, 1e-6, 1e-6)
+    pad = torch.zeros(N * (S + 1) + 3, device=DEV)
+    pad[1:1 + N * (S + 1)] = cu(rnd).flatten()
+    rnd_odd = pad[1:1 + N * (S + 1)].view(N, S + 1)                    # data pointer 4 bytes past an aligned address
+    assert rnd_odd.data_ptr() % 16 == 4
+    close(ops.sample_first_cycle(cu(near), cu(far), S, False, rnd_odd), ref, 1e-6, 1e-6)
+    M = 1000                                                           # small, unaligned: the four-per-thread variant
+    rnd_odd = pad[1:1 + M * (S + 1)].view(M, S + 1)
+    close(ops.sample_first_cycle(cu(near[:M]), cu(far[:M]), S, False, rnd_odd),
+          orc.sample_first_cycle(near[:M], far[:M], S, False, rnd[:M]), 1e-6, 1e-6)
+
+
 # ---------------------------------------------------------------------------------------------
 # f1 ray generation
 # ---------------------------------------------------------------------------------------------

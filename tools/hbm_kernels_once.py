@@ -31,5 +31,10 @@ for _ in range(3):
     w0g, mug, sgg = w.clone().requires_grad_(True), mus.clone().requires_grad_(True), sig.clone().requires_grad_(True)
     l = ops.dp_loss(t2, t0, w, w0g, mug, sgg, lt, pin, False)
     torch.autograd.grad(l, (w0g, mug, sgg))
+    # round 2: the fused DDNeRF coarse glue (compositor + (mu, sigma) head + regulariser sums), forward and backward
+    raw6 = (torch.randn(N, S, 6, device=dev, generator=g) * 0.5).requires_grad_(True)
+    dd = ops.composite_dd(raw6, t0, rays[:, 3:6], noise, 1.0, False, True, 0.01)
+    torch.autograd.grad((dd[0], dd[3], dd[4], dd[6], dd[7], dd[8]), raw6,
+                        tuple(torch.ones_like(x) for x in (dd[0], dd[3], dd[4], dd[6], dd[7], dd[8])))
 torch.cuda.synchronize()
 print("ok")

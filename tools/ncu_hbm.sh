@@ -5,7 +5,8 @@
 TAG=${1:-r1b}; N=${2:-65536}; S=${3:-128}; shift 3
 KERNELS=${@:-"composite_fwd composite_bwd sample_pdf_fast sample_pdf_mu_sigma_fast dp_loss_fwd_fast dp_loss_bwd_fast first_cycle encode_img"}
 declare -A OBJ=( [composite_fwd]=composite [composite_bwd]=composite [sample_pdf_fast]=sampler [sample_pdf_mu_sigma_fast]=sampler
-                 [dp_loss_fwd_fast]=dploss [dp_loss_bwd_fast]=dploss [first_cycle]=sampler [encode_img]=mlp_tc )
+                 [dp_loss_fwd_fast]=dploss [dp_loss_bwd_fast]=dploss [first_cycle]=sampler [encode_img]=mlp_tc
+                 [composite_dd_fwd]=composite [composite_dd_bwd]=composite )
 mkdir -p /tmp/ncu_$TAG gpurun_out
 for k in $KERNELS; do
   ncu --set full --clock-control none --import-source on -k regex:${k}_kernel -s 1 -c 1 -f \
