@@ -990,8 +990,13 @@ __device__ __forceinline__ float pack_value(const PackArgs& a, const PackEntry& 
 // One block per stage: the [n_total x 32 k] bf16 image is assembled in shared memory (element order chosen so that a warp
 // reads consecutive fp32 parameters: along k for the forward stages, along n for the transposed stages of the dX program)
 // and leaves as 16-byte stores.  Runs after every optimizer step (20 us -> 5 us per network).
-__global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
+__device__ __forceinline__ void pack_bias_row(const PackArgs& a, int l, int c);
+
+// Blocks [0, n_stages) pack one weight stage each, blocks [n_stages, n_stages + kBiasRows) one row of the fp32 table
+// (one launch per network and optimizer step instead of two).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a, int n_stages) {
     __shared__ __align__(16) uint8_t img[256 * 64];
+    if ((int)blockIdx.x >= n_stages) { pack_bias_row(a, (int)blockIdx.x - n_stages, (int)threadIdx.x); return; }
     const PackEntry E = c_pack.e[blockIdx.x];
     const int total = E.n_total * 32;
     const bool along_n = E.kind == PK_BWD || E.kind == PK_BWD_DIR;
@@ -1007,8 +1012,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
 // bias table [16][256]: rows 0..8 = layers_xyz.0-7, fc_feat; row 9 = [layers_dir.0 (128) | fc_alpha];
 // row 10 = [fc_rgb (3) | fc_mu_sigma (2)]; rows 11..13 = fc_rgb.weight rows, 14..15 = fc_mu_sigma.weight
 // rows (fp32 copies at aligned addresses, read by the backward chain's first epilogue)
-__global__ void __launch_bounds__(256) pack_bias_kernel(const PackArgs a) {
-    const int l = blockIdx.x, c = threadIdx.x;
+__device__ __forceinline__ void pack_bias_row(const PackArgs& a, int l, int c) {
     float v = 0.f;
     if (l <= 8) v = __ldg(a.p.b[l] + c);
     else if (l == 9) v = c < 128 ? __ldg(a.p.b[10] + c) : (c == 128 ? __ldg(a.p.b[9]) : 0.f);
@@ -1616,9 +1620,8 @@ extern "C" DDNERF_EXPORT int ddnerf_mlp_tc_pack(const ddnerf_mlp_params* p, int 
     TC_ENSURE("mlp_tc_pack");
     PackArgs a{*p, static_cast<uint8_t*>(wimg), bias_pack, out_channels};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    pack_weights_kernel<<<g_programs->pack.n, 256, 0, st>>>(a);
-    pack_bias_kernel<<<kBiasRows, 256, 0, st>>>(a);
-    DDNERF_LAUNCHED("mlp_tc_pack", 2);
+    pack_weights_kernel<<<g_programs->pack.n + kBiasRows, 256, 0, st>>>(a, g_programs->pack.n);
+    DDNERF_LAUNCHED("mlp_tc_pack", 1);
     return 0;
 }
 

@@ -170,7 +170,7 @@ def allreduce_gradients(buckets, world):
 class Trainer:
     """Drives ``model.run_iter`` + loss + backward + (all-reduce) + Adam, one call per iteration.
 
-    ``use_graph=True`` captures the whole iteration (20 kernel launches for mip-NeRF, 27 for DDNeRF, and many more host-side
+    ``use_graph=True`` captures the whole iteration (19 kernel launches for mip-NeRF, 25 for DDNeRF, and many more host-side
     dispatches) into ONE CUDA graph after two eager iterations and replays it from then on; the values that
     change every iteration -- learning rate, Adam bias corrections, the annealed ``gaussian_smooth_factor`` --
     are computed ON THE DEVICE by the graph's first node from a device-resident iteration counter
