@@ -347,3 +347,60 @@ def test_trainer_arena_holds_both_networks():
     assert [b.step for b in tr.buckets] == [4, 8]
     for t in tr.arena:
         assert t[pad].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("pname", ["config_blender", "config_blender_mipnerf"])
+def test_trainer_fp32_mode_gathers_into_the_arena(pname):
+    """fp32 parity mode has no gradient sink: after backward the per-parameter .grad tensors are gathered into the buckets'
+    slices of the gradient arena (FlatBucket.gather_grads) and the one Adam launch updates every network.  The gathered
+    gradient equals what autograd leaves on an identical model, and the parameters move."""
+    from oracle import ddnerf_oracle as orc
+    from ddnerf_b200.config import preset
+    from ddnerf_b200.models import models as M
+    from ddnerf_b200.rays import synth_rays
+    from ddnerf_b200.trainer import Trainer
+    dev = torch.device(DEV)
+    N, s0, s1 = 96, 16, 16
+    ro, rd, rad, _, _ = synth_rays("blender", N, seed=8)
+    g = torch.Generator().manual_seed(3)
+    target = torch.rand(N, 3, generator=g)
+    rnd = dict(t_rand=torch.rand(N, s0 + 1, generator=g), noise0=torch.randn(N, s0, generator=g),
+               u_rand=torch.rand(N, s1 + 1, generator=g), noise1=torch.randn(N, s1, generator=g))
+
+    def fresh():
+        cfg, _ = preset(pname, num_coarse=s0, num_fine=s1)
+        is_dd = cfg.nerf.type == "DDNerfModel"
+        model = getattr(M, cfg.nerf.type)(cfg)
+        model.coarse.load_state_dict(orc.init_mlp_params(is_dd, seed=51))
+        if is_dd:
+            model.fine.load_state_dict(orc.init_mlp_params(False, seed=52))
+        model.to(dev)
+        model.randoms = {k: v.to(dev) for k, v in rnd.items()}
+        return cfg, model, is_dd
+
+    args = [t.to(dev) for t in (ro, rd, rad, target)]
+    # autograd on a plain model
+    cfg, model, is_dd = fresh()
+    model.record_distributions = False
+    out = model.run_iter(*args[:3], mode="train", rgb_target=args[3])
+    tp = cfg.train_params
+    loss = sum(tp.loss_coeficients[j] * torch.nn.functional.mse_loss(out[j]["rgb"], args[3]) for j in range(2))
+    if is_dd:
+        loss = loss + tp.dp_coeficient * out[1]["dp_loss"].mean()
+    loss.backward()
+    nets = [model.coarse] + ([model.fine] if is_dd else [])
+    want = [torch.cat([p.grad.reshape(-1) for p in net.parameters()]) for net in nets]
+    # the Trainer on an identical model
+    cfg, model, is_dd = fresh()
+    tr = Trainer(model, train_iters=100, use_graph=False)
+    assert tr.arena is not None and not any(b.sink for b in tr.buckets)
+    w_before = [b.flat.clone() for b in tr.buckets]
+    loss_t, _ = tr.step(*args)
+    torch.cuda.synchronize()
+    assert abs(loss_t.item() - loss.item()) < 1e-5
+    for b, w, w0 in zip(tr.buckets, want, w_before):
+        assert not b.sink and b.step == 1
+        sc = w.abs().max().clamp(min=1e-12)
+        assert ((b.grad - w).abs().max() / sc).item() < 1e-4
+        assert (b.flat - w0).abs().max().item() > 0
+        assert all(p.grad is None for p in b.params)
